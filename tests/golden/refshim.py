@@ -1,0 +1,127 @@
+"""
+Non-invasive compatibility shim that lets the UNMODIFIED reference
+(/root/reference, read-only) import and run on this image's numpy 2.3 /
+scipy 1.18 / python 3.12.  Used ONLY by tests/golden/make_golden.py, in the
+build container; it cannot run on the GPU box (no /root/reference there) and
+nothing in tests/, bench.py or the product imports it at run time.
+
+The seven items are the ones SURVEY.md section 8(c) lists; reference files are
+never edited, everything is monkey-patched before/after `import indigo`.
+"""
+import os
+import sys
+import types
+import importlib.util
+
+REFERENCE = os.environ.get("INDIGO_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_REPO = os.path.dirname(os.path.dirname(_HERE))
+
+
+def load_reference():
+    """Returns the imported reference package `indigo` (numpy backend usable)."""
+    if "indigo" in sys.modules and getattr(sys.modules["indigo"], "_b200_shimmed", False):
+        return sys.modules["indigo"]
+    if not os.path.isdir(os.path.join(REFERENCE, "indigo")):
+        raise RuntimeError("reference not present at %s" % REFERENCE)
+
+    os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/numba_cache_indigo")
+
+    import numpy as np
+    import scipy.sparse as spp
+    import scipy.signal
+
+    # (1) scipy.sparse matrices lost the `.H` property (used np.py:125,134).
+    for cls_name in ("csr_matrix", "csc_matrix", "coo_matrix", "dia_matrix",
+                     "bsr_matrix", "lil_matrix", "dok_matrix", "spmatrix"):
+        cls = getattr(spp, cls_name, None)
+        if cls is not None and not hasattr(cls, "H"):
+            try:
+                cls.H = property(lambda self: self.conjugate().transpose())
+            except (TypeError, AttributeError):
+                pass
+    for mod_name in ("_csr", "_csc", "_coo", "_dia", "_base", "_matrix"):
+        mod = getattr(spp, mod_name, None)
+        if mod is None:
+            continue
+        for attr in dir(mod):
+            cls = getattr(mod, attr)
+            if isinstance(cls, type) and hasattr(cls, "conjugate") and hasattr(cls, "transpose") \
+                    and not hasattr(cls, "H"):
+                try:
+                    cls.H = property(lambda self: self.conjugate().transpose())
+                except (TypeError, AttributeError):
+                    pass
+
+    # (4) np.int was removed (interp.py:80).
+    if not hasattr(np, "int"):
+        np.int = int
+    # (5) scipy.signal.kaiser moved to scipy.signal.windows (backend.py:436).
+    if not hasattr(scipy.signal, "kaiser"):
+        scipy.signal.kaiser = scipy.signal.windows.kaiser
+
+    # (6) numexpr is absent (noncart.py:2,7,12): evaluate the three expressions
+    # it is given with numpy in the caller's frame.
+    if "numexpr" not in sys.modules:
+        try:
+            import numexpr  # noqa: F401
+        except ImportError:
+            ne = types.ModuleType("numexpr")
+
+            def evaluate(expr):
+                frame = sys._getframe(1)
+                scope = dict(frame.f_globals)
+                scope.update(frame.f_locals)
+                scope.update(sqrt=np.sqrt, sinh=np.sinh)
+                return eval(expr, {"__builtins__": {}}, scope)
+
+            ne.evaluate = evaluate
+            sys.modules["numexpr"] = ne
+
+    if REFERENCE not in sys.path:
+        sys.path.insert(0, REFERENCE)
+    import indigo
+    import indigo.backends
+
+    # (7) the reference's own _customcpu.c, compiled where it lies by
+    # oracle/Makefile (`make ref`), injected under its package name so that
+    # backend.py:557 finds `inspect` and sets _exwrite/_row_frac/_col_frac.
+    ref_dir = os.path.join(_REPO, "oracle", "_ref")
+    so = [f for f in os.listdir(ref_dir) if f.startswith("_customcpu")] if os.path.isdir(ref_dir) else []
+    if so:
+        spec = importlib.util.spec_from_file_location(
+            "indigo.backends._customcpu", os.path.join(ref_dir, so[0]))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        sys.modules["indigo.backends._customcpu"] = mod
+        indigo.backends._customcpu = mod
+
+    from indigo.backends.backend import Backend
+    # (2) if _customcpu is missing, _exwrite is never set (backend.py:564-567 vs :585).
+    if not so:
+        Backend.csr_matrix._exwrite = False
+
+    # (3) Backend.Zpad indexes with a list of slices (backend.py:382) which
+    # numpy 2 rejects; identical function with tuple(slc).
+    def Zpad(self, M, N, mode='center', dtype=np.dtype('complex64'), **kwargs):
+        slc = []
+        if mode == 'center':
+            for m, n in zip(M, N):
+                slc += [slice(m // 2 + int(np.ceil(-n / 2)),
+                              m // 2 + int(np.ceil(n / 2))), ]
+        elif mode == 'edge':
+            for m, n in zip(M, N):
+                slc.append(slice(n))
+        x = np.arange(np.prod(M), dtype=int).reshape(M, order='F')
+        rows = x[tuple(slc)].flatten(order='F')
+        cols = np.arange(rows.size)
+        ones = np.ones_like(cols)
+        shape = np.prod(M), np.prod(N)
+        mat = spp.coo_matrix((ones, (rows, cols)), shape=shape, dtype=dtype)
+        return self.SpMatrix(mat, **kwargs)
+    Backend.Zpad = Zpad
+
+    import logging
+    logging.getLogger("indigo.util").setLevel(logging.WARNING)   # no barrier/profile noise
+    indigo._b200_shimmed = True
+    return indigo
