@@ -1,0 +1,169 @@
+/*
+ * indigo_b200.h -- C ABI of libindigo_b200.so, the B200 (sm_100a) execution
+ * layer behind indigo's `Backend` interface.
+ *
+ * This header is the drop-in boundary.  Every entry point replaces one method
+ * of the reference's abstract backend (indigo/backends/backend.py) exactly as
+ * the reference's own GPU backend binds its libraries through ctypes
+ * (indigo/backends/cuda.py:14-18,51-62): plain pointers and sizes, no C++ or
+ * torch types, `int` status returns.  INTEGRATION.md shows the ctypes stub a
+ * maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - status: 0 = OK; >0 = cudaError_t; <0 = IB200_E_* below.  Nothing throws.
+ *     ib200_last_error() returns a thread-local message for the last failure.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *     Compute entry points enqueue work and DO NOT synchronise, except the few
+ *     that return a host scalar (documented per function).
+ *   - all matrices are complex64 (interleaved re,im floats), column-major,
+ *     addressed as ptr[row + col*ld]; `ld` is in ELEMENTS and may be far larger
+ *     than the row count (views into indigo's scratch arena, SURVEY.md
+ *     landmine 4).  Pointers need only be 8-byte aligned.
+ *   - beta == 0 means "overwrite": Y is never read (the arena is uninitialised,
+ *     indigo/transforms.py:73-76).
+ *   - sparse indices are 0-based int32 (indigo/backends/backend.py:539,549-550).
+ */
+#ifndef INDIGO_B200_H
+#define INDIGO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IB200_E_INVALID   (-1)   /* bad argument                               */
+#define IB200_E_UNSUPPORTED (-2) /* valid request this build cannot serve      */
+#define IB200_E_NOMEM     (-3)   /* host allocation failed                     */
+
+#define IB200_FFT_FORWARD (-1)   /* same sign convention as cuda.py:427-428    */
+#define IB200_FFT_INVERSE (+1)
+
+const char *ib200_last_error(void);
+int ib200_version(void);
+/* Fills sm_count, max opt-in shared memory per block, L2 bytes, total global
+ * memory for device `dev`; any out pointer may be NULL. */
+int ib200_device_info(int dev, int *sm_count, int64_t *smem_optin, int64_t *l2_bytes, int64_t *mem_bytes);
+/* How many kernels this library has launched since load (bench.py's
+ * `gpu_launches`); reset with ib200_launch_count_reset(). */
+int64_t ib200_launch_count(void);
+void ib200_launch_count_reset(void);
+
+/* ------------------------------------------------------------------ arrays
+ * Backend.dndarray._copy_from/_copy_to/_copy/_zero, backend.py:187-215;
+ * pitched-copy model of cuda.py:127-181.  kind: 0 = D2D, 1 = H2D, 2 = D2H.
+ * Asynchronous on `stream`; H2D/D2H from pageable memory behave like
+ * cudaMemcpy2DAsync (staged).  ib200_stream_sync is Backend.barrier(),
+ * backend.py:246 / cuda.py:120-121. */
+int ib200_copy2d(void *stream, void *dst, int64_t dpitch_bytes, const void *src, int64_t spitch_bytes,
+                 int64_t width_bytes, int64_t height, int kind);
+int ib200_memset0(void *stream, void *dst, int64_t nbytes);
+int ib200_stream_sync(void *stream);
+
+/* ------------------------------------------------------------------ BLAS-1
+ * Backend.axpby / scale / dot / norm2, backend.py:453-467 (oracle np.py:53-74).
+ * n counts complex elements. */
+int ib200_caxpby(void *stream, int64_t n, float beta_re, float beta_im, void *y,
+                 float alpha_re, float alpha_im, const void *x);            /* y = beta*y + alpha*x */
+int ib200_cscal(void *stream, int64_t n, float alpha_re, float alpha_im, void *x);
+/* Device-resident results (no sync): out[0..1] = sum conj(x)*y as doubles. */
+int ib200_cdotc_dev(void *stream, int64_t n, const void *x, const void *y, double *dev_out2);
+/* out[0] = sum |x|^2 as a double. */
+int ib200_scnrm2sq_dev(void *stream, int64_t n, const void *x, double *dev_out1);
+/* Host-returning forms used by Backend.dot / Backend.norm2: run the reduction,
+ * copy the scalar back and synchronise `stream`.  *host_re = Re(x^H y) (the
+ * reference returns only the real part, np.py:64); *host_out = ||x||^2
+ * (SQUARED, np.py:69). */
+int ib200_cdotc(void *stream, int64_t n, const void *x, const void *y, double *host_re, double *host_im);
+int ib200_scnrm2sq(void *stream, int64_t n, const void *x, double *host_out);
+
+/* Fused CG vector updates for Backend.cg, backend.py:666-679.  All scalars
+ * live in device memory (doubles) so one iteration needs no host round trip:
+ *   ib200_cg_xr : alpha = rr/pAp;  x += alpha*p;  r -= alpha*Ap;  r2 = ||r||^2
+ *   ib200_cg_p  : beta = r2/rr;    p = beta*p + r;                 rr = r2
+ * `scal` points at 4 device doubles {rr, Re(p^H Ap), Im(p^H Ap), r2}; fill
+ * scal[1..2] with ib200_cdotc_dev(stream, n, p, Ap, scal + 1). */
+int ib200_cg_xr(void *stream, int64_t n, void *x, void *r, const void *p, const void *Ap, double *scal);
+int ib200_cg_p(void *stream, int64_t n, void *p, const void *r, double *scal);
+
+/* ------------------------------------------------------------------ sparse
+ * Backend.ccsrmm, backend.py:514-519 (oracle np.py:120-127; native reference
+ * _customcpu.c:14-114, _customgpu.cu:49-81, cuda.py:582-596):
+ *   adjoint == 0 : Y(m x ncols) = alpha * A      * X(k x ncols) + beta * Y
+ *   adjoint != 0 : Y(k x ncols) = alpha * A^H    * X(m x ncols) + beta * Y
+ * A is m x k CSR (rowptr[m+1], colind[nnz], vals[nnz]; nnz is passed like
+ * cusparseCcsrmm's, cuda.py:590, and only steers the thread-per-row split).
+ * `exwrite` promises
+ * that no two stored entries share a column (scatter without atomics). */
+int ib200_ccsrmm(void *stream, int adjoint, int exwrite, int64_t m, int64_t k, int64_t ncols, int64_t nnz,
+                 float alpha_re, float alpha_im, const void *vals, const int32_t *colind, const int32_t *rowptr,
+                 const void *X, int64_t ldx, float beta_re, float beta_im, void *Y, int64_t ldy);
+/* The inspector of _customcpu.c:179-215 on the device: out = {rows with >=1
+ * entry, columns with >=1 entry, exwrite flag, max entries in one column}.
+ * `work` is k int32 of device scratch.  Synchronises `stream`. */
+int ib200_csr_inspect(void *stream, int64_t m, int64_t k, const int32_t *colind, const int32_t *rowptr,
+                      int32_t *work, int64_t host_out[4]);
+/* Device-side conjugate transpose of a CSR matrix (the "stored adjoint" used
+ * for non-exclusive-write adjoints).  t_rowptr[k+1], t_colind[nnz], t_vals[nnz]
+ * are caller-allocated device buffers; `work` is k+1 int32 of device scratch.
+ * Output rows are sorted by column.  Synchronises `stream`. */
+int ib200_csr_transpose_conj(void *stream, int64_t m, int64_t k, int64_t nnz,
+                             const void *vals, const int32_t *colind, const int32_t *rowptr,
+                             void *t_vals, int32_t *t_colind, int32_t *t_rowptr, int32_t *work);
+/* Backend.cdiamm, backend.py:521-526 (oracle np.py:129-136; _customgpu.cu:83-143).
+ * A is m x k in DIA form; data is (ncolsA x noffsets) column-major where
+ * ncolsA = k, i.e. scipy's dia.data transposed (backend.py:610).
+ *   adjoint == 0 : Y(m x n) = alpha*A*X(k x n) + beta*Y
+ *   adjoint != 0 : Y(k x n) = alpha*A^H*X(m x n) + beta*Y */
+int ib200_cdiamm(void *stream, int adjoint, int64_t m, int64_t k, int64_t ncols, int64_t noffsets,
+                 const int32_t *offsets, const void *data, float alpha_re, float alpha_im,
+                 const void *X, int64_t ldx, float beta_re, float beta_im, void *Y, int64_t ldy);
+/* Backend.onemm, backend.py:528-533 (oracle np.py:95-97; _customgpu.cu:15-47):
+ * Y(m x n) = beta*Y + alpha * ones(m,k) * X(k x n). */
+int ib200_onemm(void *stream, int64_t m, int64_t ncols, int64_t k, float alpha_re, float alpha_im,
+                const void *X, int64_t ldx, float beta_re, float beta_im, void *Y, int64_t ldy);
+/* Backend.max, backend.py:734-736 (np.py:141-145; _customgpu.cu:7-13):
+ * arr = max(arr, val) over nfloats floats (real and imaginary parts alike). */
+int ib200_fmax(void *stream, int64_t nfloats, float val, void *arr);
+
+/* ------------------------------------------------------------------ FFT
+ * Backend.fftn / ifftn, backend.py:497-509 (oracle np.py:102-115; cuFFT
+ * binding cuda.py:470-498): unscaled forward and UNSCALED inverse C2C over the
+ * first `ndim` (1..3) axes of a column-major (d0[,d1[,d2]], batch) array with
+ * contiguous batches.  Out of place or in place (y == x).  Any lengths: radices
+ * 2,3,4,5,7,8,11,13,16 are specialised, other prime factors use a generic
+ * butterfly.  No workspace (Backend._fft_workspace_size -> 0). */
+typedef struct ib200_fft_plan_s *ib200_fft_plan;
+int ib200_fft_plan_create(ib200_fft_plan *plan, int ndim, const int64_t *dims, int64_t batch);
+int ib200_fft_plan_destroy(ib200_fft_plan plan);
+/* Writes the radix sequence of axis `axis` into radices[0..max) and returns
+ * the number of stages (host only, no device needed) or a negative error. */
+int ib200_fft_plan_describe(ib200_fft_plan plan, int axis, int *radices, int max);
+int ib200_fft_exec(ib200_fft_plan plan, void *stream, void *y, const void *x, int direction);
+/* Fused variants (the north-star's "fused
+ * elementwise"): d_in / d_out are optional length-prod(dims) complex64
+ * diagonals applied on the first pass's load / the last pass's store,
+ * broadcast over the batch; conj_* conjugates the diagonal. */
+int ib200_fft_exec_diag(ib200_fft_plan plan, void *stream, void *y, const void *x, int direction,
+                        const void *d_in, int conj_in, const void *d_out, int conj_out);
+
+/* ------------------------------------------------------------------ dense
+ * Backend.cgemm, backend.py:481-485 (oracle np.py:76-87; cuda.py:314-329):
+ *   conjtrans == 0 : Y(m x n) = alpha * M(m x k)     * X(k x n) + beta*Y
+ *   conjtrans != 0 : Y(m x n) = alpha * M(k x m)^H   * X(k x n) + beta*Y
+ * Backend.csymm, backend.py:487-491 (np.py:89-90; cuda.py:355-366), M real
+ * symmetric (stored full, complex64):
+ *   left  != 0 : Y(m x n) = alpha * M(m x m) * X(m x n) + beta*Y
+ *   left  == 0 : Y(m x n) = alpha * X(m x n) * M(n x n) + beta*Y */
+int ib200_cgemm(void *stream, int conjtrans, int64_t m, int64_t n, int64_t k, float alpha_re, float alpha_im,
+                const void *M, int64_t ldm, const void *X, int64_t ldx, float beta_re, float beta_im,
+                void *Y, int64_t ldy);
+int ib200_csymm(void *stream, int left, int64_t m, int64_t n, float alpha_re, float alpha_im,
+                const void *M, int64_t ldm, const void *X, int64_t ldx, float beta_re, float beta_im,
+                void *Y, int64_t ldy);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INDIGO_B200_H */
