@@ -148,6 +148,31 @@ int ib200_fft_exec(ib200_fft_plan plan, void *stream, void *y, const void *x, in
 int ib200_fft_exec_diag(ib200_fft_plan plan, void *stream, void *y, const void *x, int direction,
                         const void *d_in, int conj_in, const void *d_out, int conj_out);
 
+/* ------------------------------------------------------------------ operator construction on the device
+ * Setup-time replacements for the host construction of the two sparse factors
+ * of the -O3 SENSE tree (indigo/interp.py:19-80 + scipy COO->CSR + the -O2
+ * products of indigo/transforms.py:86-96 / examples/pics.py:111-126).  All
+ * buffers are device memory; results are ordinary CSR arrays for ib200_ccsrmm.
+ *
+ * Gridding matrix G' (m samples x prod(grid)):  count -> exclusive scan -> fill.
+ *   coord     (3, m) doubles, coord[d + 3*i] in cycles/FOV
+ *   table     Kaiser-Bessel half window (ntable doubles), backend.py:435-436
+ *   rowweight optional m floats (sqrt density compensation) or NULL
+ *   colscale  optional prod(grid) complex64 = diagonal of mod*scale, or NULL */
+int ib200_kb_count(void *stream, int64_t m, const double *coord, const int64_t grid[3], double width,
+                   int32_t *counts);
+int ib200_exclusive_scan_i32(void *stream, int64_t n, const int32_t *in, int32_t *out /* n+1, synchronises */);
+int ib200_kb_fill(void *stream, int64_t m, const double *coord, const int64_t grid[3], double width,
+                  const double *table, int ntable, const float *rowweight, const void *colscale,
+                  const int32_t *rowptr, int32_t *colind, void *vals);
+/* Stored adjoint P^H (nvox x ncoils*ogrid) of P = kron(I, mod*zpad*apod) * vstack(maps):
+ * row r holds conj(q[r]*maps[r,c]) at column c*ogrid + zp[r] for every coil c with a
+ * non-zero product.  maps is (nvox, ncoils) column-major, q = mod[zp]*apod, zp the
+ * zero-padded position of voxel r (backend.py:371-387). */
+int ib200_sense_ph_count(void *stream, int64_t nvox, int ncoils, const void *maps, const void *q, int32_t *counts);
+int ib200_sense_ph_fill(void *stream, int64_t nvox, int ncoils, int64_t ogrid, const void *maps, const void *q,
+                        const int32_t *zp, const int32_t *rowptr, int32_t *colind, void *vals);
+
 /* ------------------------------------------------------------------ dense
  * Backend.cgemm, backend.py:481-485 (oracle np.py:76-87; cuda.py:314-329):
  *   conjtrans == 0 : Y(m x n) = alpha * M(m x k)     * X(k x n) + beta*Y

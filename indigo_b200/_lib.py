@@ -36,6 +36,11 @@ SIGNATURES = {
     "ib200_ccsrmm": (_i, [_vp, _i, _i, _i64, _i64, _i64, _i64, _f, _f, _vp, _vp, _vp, _vp, _i64, _f, _f, _vp, _i64]),
     "ib200_csr_inspect": (_i, [_vp, _i64, _i64, _vp, _vp, _vp, POINTER(_i64)]),
     "ib200_csr_transpose_conj": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ib200_kb_count": (_i, [_vp, _i64, _vp, POINTER(_i64), c_double, _vp]),
+    "ib200_exclusive_scan_i32": (_i, [_vp, _i64, _vp, _vp]),
+    "ib200_kb_fill": (_i, [_vp, _i64, _vp, POINTER(_i64), c_double, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "ib200_sense_ph_count": (_i, [_vp, _i64, _i, _vp, _vp, _vp]),
+    "ib200_sense_ph_fill": (_i, [_vp, _i64, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ib200_cdiamm": (_i, [_vp, _i, _i64, _i64, _i64, _i64, _vp, _vp, _f, _f, _vp, _i64, _f, _f, _vp, _i64]),
     "ib200_onemm": (_i, [_vp, _i64, _i64, _i64, _f, _f, _vp, _i64, _f, _f, _vp, _i64]),
     "ib200_fmax": (_i, [_vp, _i64, _f, _vp]),

@@ -175,16 +175,39 @@ def make_backend_class(Base, name="B200Backend"):
             self.values = backend.copy_array(A.data, name=name + ".data")
             self.shape, self.dtype = A.shape, A.dtype
             self._adj = None
-            m, k = A.shape
+            self._inspect_device()
+
+        @classmethod
+        def from_device(cls, backend, shape, rowPtrs, colInds, values, name='mat'):
+            """Wraps CSR arrays that already live on the device (built by ib200_kb_fill /
+            ib200_sense_ph_fill) and runs the same device inspector."""
+            self = cls.__new__(cls)
+            self._backend, self._name = backend, name
+            self.rowPtrs, self.colInds, self.values = rowPtrs, colInds, values
+            self.shape, self.dtype = tuple(int(v) for v in shape), _C64
+            self._adj = None
+            self._inspect_device()
+            return self
+
+        def _inspect_device(self):
+            backend, (m, k) = self._backend, self.shape
             out = (ctypes.c_int64 * 4)()
-            work = backend.empty_array((max(k, 1),), np.dtype('int32'), name=name + ".inspect")
+            work = backend.empty_array((max(k, 1),), np.dtype('int32'), name=self._name + ".inspect")
             backend._lib.csr_inspect(backend._stream, m, k, self.colInds.ptr, self.rowPtrs.ptr, work.ptr, out)
             self._row_frac = out[0] / m if m else 1.0
             self._col_frac = out[1] / k if k else 1.0
             self._exwrite = int(out[2])
             self._max_col_count = int(out[3])
-            log.debug("matrix %s: %d%% nonzero rows, %d%% nonzero cols, exwrite=%d", name,
+            log.debug("matrix %s: %d%% nonzero rows, %d%% nonzero cols, exwrite=%d", self._name,
                       100 * self._row_frac, 100 * self._col_frac, self._exwrite)
+
+        def _use_stored_adjoint(self):
+            mode = self._backend.stored_adjoints
+            if mode == 'auto':
+                # long rows (gridding stencils): one RED.64 per update beats gathering through a
+                # transposed matrix whose rows are short and whose operand rows are scattered
+                return self.shape[0] > 0 and (int(self.values.size) / self.shape[0]) < 32
+            return bool(mode)
 
         def _stored_adjoint(self):
             if self._adj is None:
@@ -204,7 +227,7 @@ def make_backend_class(Base, name="B200Backend"):
             assert y.dtype == _C64, "Bad dtype: expected compelx64, got %s" % y.dtype
             assert self.values.dtype == _C64
             b = self._backend
-            if self._exwrite or not b.stored_adjoints:
+            if self._exwrite or not self._use_stored_adjoint():
                 return b.ccsrmm(y, self.shape, self.colInds, self.rowPtrs, self.values, x,
                                 alpha=alpha, beta=beta, adjoint=True, exwrite=self._exwrite)
             t_ptr, t_ind, t_val = self._stored_adjoint()
@@ -213,7 +236,7 @@ def make_backend_class(Base, name="B200Backend"):
     class B200Backend(Base):
         dndarray = B200Array
         csr_matrix = B200Csr
-        stored_adjoints = True          # keep A^H in CSR for non-exclusive-write matrices
+        stored_adjoints = 'auto'        # True / False / 'auto': keep A^H in CSR for non-exclusive-write matrices
 
         def __init__(self, device_id=0, lib=None):
             super().__init__(device_id)

@@ -327,6 +327,10 @@ static int exclusive_scan(cudaStream_t s, int64_t n, const int32_t *in, int32_t 
     return 0;
 }
 
+int exclusive_scan_public(cudaStream_t s, int64_t n, const int32_t *in, int32_t *out) {
+    return exclusive_scan(s, n, in, out, out + n);
+}
+
 // unsorted fill: cursor[c] starts at t_rowptr[c]
 __global__ void __launch_bounds__(256) transpose_fill_kernel(int64_t m, const c64 *__restrict__ vals,
                                                              const int32_t *__restrict__ colind,

@@ -63,3 +63,135 @@ def sqrt_dcf(coord):
     c = np.asarray(coord, dtype=np.float64)
     c = c.reshape((3, -1), order='F')
     return np.sqrt(np.sqrt((c ** 2).sum(axis=0))).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------
+# Device-side construction
+# ---------------------------------------------------------------------------
+def _fftc_mod_times_scale(oN):
+    """Diagonal of mod*scale as the -O2 realisation produces it: mod = exp(2 pi i sum_d
+    (i_d - c_d/2) c_d/n_d) in float64 (backend.py:357-363) cast to complex64, times the
+    complex64 cast of 1/sqrt(prod(oN)) (backend.py:349-351).  Evaluated slab by slab so
+    that a 416^3 grid never needs the full float64 mgrid."""
+    n = int(np.prod(oN))
+    terms = []
+    for d in range(3):
+        c = oN[d] // 2
+        terms.append((np.arange(oN[d]) - c / 2.0) * (c / oN[d]))
+    scl = np.complex64(np.complex128(1.0) / np.sqrt(n))
+    out = np.empty(oN, dtype=_C64, order='F')
+    txy = (0 + terms[0][:, None]) + terms[1][None, :]
+    for z in range(oN[2]):
+        ph = txy + terms[2][z]
+        out[:, :, z] = np.exp(1j * 2.0 * np.pi * ph).astype(_C64) * scl
+    return out.reshape(-1, order='F')
+
+
+def _fftc_mod(oN):
+    terms = []
+    for d in range(3):
+        c = oN[d] // 2
+        terms.append((np.arange(oN[d]) - c / 2.0) * (c / oN[d]))
+    ph = ((0 + terms[0][:, None, None]) + terms[1][None, :, None]) + terms[2][None, None, :]
+    return np.exp(1j * 2.0 * np.pi * ph).astype(_C64)
+
+
+class DeviceBuiltSpMatrix(object):
+    """Mixin for SpMatrix leaves whose device matrix is produced by CUDA kernels from
+    the problem description instead of being uploaded from a scipy matrix."""
+
+
+def sense_operator_device(B, N, coord, maps, oversamp=2.0, weights=None, width=3, n=128):
+    """Same operator, same -O3 tree shape and the same six backend calls per A^H A as
+    sense_operator(), but G' and P^H are built on the GPU (ib200_kb_* / ib200_sense_ph_*)
+    straight into device CSR arrays: no COO triplets, no scipy products, no 10 GB upload.
+    Needed at BASELINE.json's full sizes (416^3 grid, 6.8 M samples: 853 M stored entries).
+    tests/test_gpu_sense.py checks structure (bit-identical) and values against the
+    host-built matrices."""
+    import ctypes
+    from scipy.signal.windows import kaiser
+    from .host.noncart import rolloff3
+    from .host import optree as op
+
+    lib, s = B._lib, B._stream
+    N = tuple(int(v) for v in N)
+    C = int(maps.shape[3])
+    if isinstance(oversamp, tuple):
+        omin, os3 = min(oversamp), oversamp
+    else:
+        omin, os3 = oversamp, (oversamp,) * 3
+    oN = tuple(int(a * o) for a, o in zip(N, os3))
+    on, nvox = int(np.prod(oN)), int(np.prod(N))
+    beta = np.pi * np.sqrt(((width * 2. / omin) * (omin - 0.5)) ** 2 - 0.8)
+    table = np.ascontiguousarray(kaiser(2 * n + 1, beta)[n:], dtype=np.float64)
+
+    # ---- G' = interp * (mod * scale) -------------------------------------------------
+    coord = np.asarray(coord)
+    c3 = np.asfortranarray(coord.reshape((3, -1), order='F').astype(np.float64))
+    m = c3.shape[1]
+    grid = (ctypes.c_int64 * 3)(*oN)
+    coord_d = B.copy_array(c3)
+    table_d = B.copy_array(table)
+    counts = B.empty_array((max(m, 1),), np.dtype('int32'))
+    lib.kb_count(s, m, coord_d.ptr, grid, float(width), counts.ptr)
+    g_ptr = B.empty_array((m + 1,), np.dtype('int32'), name='interp*mod*scale.rowPtrs')
+    lib.exclusive_scan_i32(s, m, counts.ptr, g_ptr.ptr)
+    nnz = int(g_ptr[m:m + 1].to_host()[0])
+    g_ind = B.empty_array((max(nnz, 1),), np.dtype('int32'), name='interp*mod*scale.colInds')
+    g_val = B.empty_array((max(nnz, 1),), _C64, name='interp*mod*scale.data')
+    colscale_d = B.copy_array(_fftc_mod_times_scale(oN))
+    w_d = None
+    if weights is not None:
+        w_d = B.copy_array(np.ascontiguousarray(np.asarray(weights, dtype=np.float32).reshape(-1)))
+    lib.kb_fill(s, m, coord_d.ptr, grid, float(width), table_d.ptr, int(table.size),
+                w_d.ptr if w_d is not None else None, colscale_d.ptr, g_ptr.ptr, g_ind.ptr, g_val.ptr)
+    B.barrier()
+    del colscale_d, coord_d, counts
+    Gd = B.csr_matrix.from_device(B, (m, on), g_ptr, g_ind[0:nnz], g_val[0:nnz], name='interp*mod*scale')
+
+    # ---- P^H, stored adjoint of kron(I_C, mod*zpad*apod) * vstack(maps) ----------------
+    cut = tuple(slice(a // 2 + int(np.ceil(-b / 2)), a // 2 + int(np.ceil(b / 2))) for a, b in zip(oN, N))
+    lin = np.arange(on, dtype=np.int64).reshape(oN, order='F')
+    zp = np.ascontiguousarray(lin[cut].flatten(order='F').astype(np.int32))
+    del lin
+    mod_at = _fftc_mod(oN)[cut].flatten(order='F')
+    apod = rolloff3(omin, width, beta, N).flatten(order='F').astype(_C64)
+    q = np.ascontiguousarray((mod_at * np.complex64(1)) * apod)             # (mod @ zpad) @ apod
+    maps_f = np.asfortranarray(maps.reshape((nvox, C), order='F').astype(_C64))
+    maps_d, q_d, zp_d = B.copy_array(maps_f), B.copy_array(q), B.copy_array(zp)
+    counts = B.empty_array((nvox,), np.dtype('int32'))
+    lib.sense_ph_count(s, nvox, C, maps_d.ptr, q_d.ptr, counts.ptr)
+    p_ptr = B.empty_array((nvox + 1,), np.dtype('int32'), name='P.H.rowPtrs')
+    lib.exclusive_scan_i32(s, nvox, counts.ptr, p_ptr.ptr)
+    pnnz = int(p_ptr[nvox:nvox + 1].to_host()[0])
+    p_ind = B.empty_array((max(pnnz, 1),), np.dtype('int32'), name='P.H.colInds')
+    p_val = B.empty_array((max(pnnz, 1),), _C64, name='P.H.data')
+    lib.sense_ph_fill(s, nvox, C, on, maps_d.ptr, q_d.ptr, zp_d.ptr, p_ptr.ptr, p_ind.ptr, p_val.ptr)
+    B.barrier()
+    del maps_d, q_d, zp_d, counts
+    Pd = B.csr_matrix.from_device(B, (nvox, C * on), p_ptr, p_ind[0:pnnz], p_val[0:pnnz],
+                                  name='((x)mod*zpad*apod)*+.H')
+
+    # ---- the -O3 tree around them (shape of examples/pics.py -O3 output, SURVEY 3.1) -----
+    class _DevSp(op.SpMatrix, DeviceBuiltSpMatrix):
+        def __init__(self, backend, dev, name):
+            op.Operator.__init__(self, backend, name=name)
+            self._matrix, self._matrix_d = None, dev
+            self._allow_exwrite, self._use_dia = True, False
+
+        shape = property(lambda self: self._matrix_d.shape)
+        dtype = property(lambda self: _C64)
+        nnz = property(lambda self: int(self._matrix_d.nnz))
+
+        def _mem_usage(self, ncols=1):
+            return int(self._matrix_d.values.nbytes)
+
+        def _get_or_create_device_matrix(self):
+            return self._matrix_d
+
+    Gn = _DevSp(B, Gd, 'interp*mod*scale')
+    Pn = _DevSp(B, Pd, '((x)mod*zpad*apod)*+.H')
+    F = B.UnscaledFFT(oN, _C64, name='fft')
+    A = B.KronI(C, Gn) * (B.KronI(C, F) * Pn.H)
+    A._name = 'SENSE1'
+    return A.optimize([])

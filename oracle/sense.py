@@ -240,6 +240,56 @@ class SenseOperator:
         out[...] = self.normal(inp).reshape(out.shape, order="F")
 
 
+class SenseTruth64:
+    """complex128 evaluation of the same -O3 tree (same CSR matrices promoted to
+    double, numpy FFT in double): the arbiter when the complex64 oracle and the
+    CUDA path disagree, and the yardstick for the oracle's own rounding noise
+    (SURVEY.md section 8c "oracle hygiene")."""
+
+    def __init__(self, op):
+        self.op = op
+        self.G = op.G.astype(np.complex128)
+        self.PH = op.PH.astype(np.complex128)
+
+    def normal(self, x):
+        op, C = self.op, self.op.C
+        t = (self.PH.conjugate().transpose() @ np.asarray(x, dtype=np.complex128).reshape(-1, 1))
+        t = np.fft.fftn(t.reshape(op.oN + (C,), order="F"), axes=(0, 1, 2)).reshape((-1, C), order="F")
+        g = self.G.conjugate().transpose() @ (self.G @ t)
+        g = np.fft.ifftn(g.reshape(op.oN + (C,), order="F"), axes=(0, 1, 2)) * np.prod(op.oN)
+        return self.PH @ g.reshape((-1, 1), order="F")
+
+    def cg(self, b, lamda, maxiter):
+        """Backend.cg's recurrence (backend.py:666-679) in double; returns all iterates."""
+        x = np.zeros(np.shape(b), dtype=np.complex128)
+        r = np.asarray(b, dtype=np.complex128).copy()
+        p = r.copy()
+        rr = np.vdot(r, r).real
+        out = []
+        for _ in range(maxiter):
+            Ap = self.normal(p).reshape(p.shape) + lamda * p
+            a = rr / np.vdot(p, Ap).real
+            x = x + a * p
+            r = r - a * Ap
+            r2 = np.vdot(r, r).real
+            p = r + (r2 / rr) * p
+            rr = r2
+            out.append(x.copy())
+        return out
+
+
+def spectral_norm(op, iters=15, seed=0):
+    """Power-iteration estimate of ||A^H A||_2 (used to scale lamda in the CG protocol)."""
+    rs = np.random.RandomState(seed)
+    v = (rs.rand(op.shape[1], 1) + 1j * rs.rand(op.shape[1], 1)).astype(C64)
+    nv = 1.0
+    for _ in range(iters):
+        v = op.normal(v)
+        nv = float(np.linalg.norm(v))
+        v = (v / nv).astype(C64)
+    return nv
+
+
 def sqrt_dcf(coord):
     """sqrt(|k|) row weights of the well-conditioned CG protocol."""
     c = flat_coord(coord).astype(np.float64)

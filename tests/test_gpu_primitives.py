@@ -66,7 +66,7 @@ def test_array_slice_1d(B, s):
     np.testing.assert_array_equal(d[s:].to_host(), a[s:])
 
 
-@pytest.mark.parametrize("M,N,xb,xe,yb,ye", product([6, 7], [8, 9], [0, 2], [4, 5], [0, 1], [6, 7]))
+@pytest.mark.parametrize("M,N,xb,xe,yb,ye", list(product([6, 7], [8, 9], [0, 2], [4, 5], [0, 1], [6, 7])))
 def test_array_slice_2d(B, M, N, xb, xe, yb, ye):
     a = synth.rand64c(np.random.RandomState(M * N), M, N)
     d = B.copy_array(a)
@@ -80,7 +80,7 @@ def test_array_slice_2d(B, M, N, xb, xe, yb, ye):
 
 
 # --------------------------------------------------------------------------- BLAS-1
-@pytest.mark.parametrize("n,alpha,beta", product([1, 10, 23, 129, 100001], [0.0, 1.0, -2.1 + 3j], [0.0, 0.5, 1.0, 1.5 - 1j]))
+@pytest.mark.parametrize("n,alpha,beta", list(product([1, 10, 23, 129, 100001], [0.0, 1.0, -2.1 + 3j], [0.0, 0.5, 1.0, 1.5 - 1j])))
 def test_axpby(B, n, alpha, beta):
     rs = np.random.RandomState(n)
     x, y = synth.rand64c(rs, n), synth.rand64c(rs, n)
@@ -132,7 +132,7 @@ def _rand_csr(rs, m, n, density):
     return A
 
 
-@pytest.mark.parametrize("M,N,Kc,density", product([23, 45], [45, 23], [1, 8, 9, 17], [0.01, 0.1, 0.5]))
+@pytest.mark.parametrize("M,N,Kc,density", list(product([23, 45], [45, 23], [1, 8, 9, 17], [0.01, 0.1, 0.5])))
 def test_csr_matrix(B, M, N, Kc, density):
     rs = np.random.RandomState(M * N + Kc)
     A = _rand_csr(rs, M, N, density)
@@ -154,7 +154,7 @@ def test_csr_matrix(B, M, N, Kc, density):
     B.stored_adjoints = True
 
 
-@pytest.mark.parametrize("M,N,Kc,alpha,beta", product([23, 45], [1, 8, 9, 17], [18, 19], [0.0, 0.5, 1.5], [0.0, 1.0, 1.5]))
+@pytest.mark.parametrize("M,N,Kc,alpha,beta", list(product([23, 45], [1, 8, 9, 17], [18, 19], [0.0, 0.5, 1.5], [0.0, 1.0, 1.5])))
 def test_exw_csr_matrix(B, M, N, Kc, alpha, beta):
     rs = np.random.RandomState(M + N + Kc)
     counts = rs.randint(0, 2, Kc)
@@ -278,7 +278,7 @@ def test_fft_full_size_axis_roundtrip(B):
 
 
 # --------------------------------------------------------------------------- dense, one, dia, max
-@pytest.mark.parametrize("m,n,k,alpha,beta,forward", product([10, 23, 129, 144], [10, 144], [23, 129], [1, 0.5 + 0.5j, 0.0], [0, 0.5], [True, False]))
+@pytest.mark.parametrize("m,n,k,alpha,beta,forward", list(product([10, 23, 129, 144], [10, 144], [23, 129], [1, 0.5 + 0.5j, 0.0], [0, 0.5], [True, False])))
 def test_cgemm(B, m, n, k, alpha, beta, forward):
     rs = np.random.RandomState(m * n + k)
     y, M, x = synth.rand64c(rs, m, n), synth.rand64c(rs, m, k), synth.rand64c(rs, k, n)
@@ -290,7 +290,7 @@ def test_cgemm(B, m, n, k, alpha, beta, forward):
     assert relerr(yd.to_host(), want) < 1e-5 or np.allclose(yd.to_host(), want, atol=1e-4)
 
 
-@pytest.mark.parametrize("m,k,alpha,beta,left", product([2, 5, 6, 40], [1, 3], [0.0, 1.5], [0.0, 0.5], [True, False]))
+@pytest.mark.parametrize("m,k,alpha,beta,left", list(product([2, 5, 6, 40], [1, 3], [0.0, 1.5], [0.0, 0.5], [True, False])))
 def test_csymm(B, m, k, alpha, beta, left):
     rs = np.random.RandomState(m + k)
     S = synth.rand64c(rs, m, m); S = np.asfortranarray(S + S.T); S.imag = 0
@@ -321,7 +321,7 @@ def test_onemm_dia_max_golden(B, golden_dir):
     assert abs(B.norm2(xd) - float(g["b1_nrm2"])) < 1e-4
 
 
-@pytest.mark.parametrize("M,Kd,N,alpha,beta,noff", product([23, 45], [45, 23], [1, 9], [0.5, 1.5], [0.0, 1.5], [1, 4]))
+@pytest.mark.parametrize("M,Kd,N,alpha,beta,noff", list(product([23, 45], [45, 23], [1, 9], [0.5, 1.5], [0.0, 1.5], [1, 4])))
 def test_dia_matrix(B, M, Kd, N, alpha, beta, noff):
     rs = np.random.RandomState(M * Kd + N + noff)
     offs = np.array(sorted(set(rs.randint(-Kd, M + Kd, size=noff))))
@@ -335,7 +335,7 @@ def test_dia_matrix(B, M, Kd, N, alpha, beta, noff):
     np.testing.assert_allclose(xd.to_host(), beta * x + alpha * (A.conj().T @ y), atol=1e-5)
 
 
-@pytest.mark.parametrize("val,N", product([-1.5, 0, 0.5, 1.5], [4, 5, 1000]))
+@pytest.mark.parametrize("val,N", list(product([-1.5, 0, 0.5, 1.5], [4, 5, 1000])))
 def test_max(B, val, N):
     a = synth.rand64c(np.random.RandomState(N), N)
     ad = B.copy_array(a); B.max(val, ad)

@@ -140,10 +140,69 @@ def test_reduced_cfg3_against_oracle(B):
     want = ref.normal(x)
     assert relerr(AHA * x, want) < TOL
     b = (want / np.abs(want).max()).astype(C64)
-    lam = 1e-2 * float(np.abs(np.vdot(x, want)) / np.vdot(x, x).real)
-    mine, theirs = [], []
-    xs = np.zeros_like(b, order='F')
-    B.cg(AHA, b, xs, lamda=lam, maxiter=50, tol=0.0, iterates=mine)
-    K.cg(ref.normal_into, b, np.zeros_like(b), lamda=lam, tol=0.0, maxiter=50, iterates=theirs)
+    nrm = osense.spectral_norm(ref)
+
+    def run(lam):
+        mine, theirs = [], []
+        B.cg(AHA, b, np.zeros_like(b, order='F'), lamda=lam, maxiter=50, tol=0.0, iterates=mine)
+        K.cg(ref.normal_into, b, np.zeros_like(b), lamda=lam, tol=0.0, maxiter=50, iterates=theirs)
+        return mine, theirs
+
+    # (1) well-conditioned protocol: every one of the 50 iterates within 1e-5 of the oracle's.
+    # lamda = 0.05*||A^H A||_2 keeps the complex64 oracle itself within 1.3e-6 of the fp64
+    # recurrence (measured, DESIGN.md "CG parity protocol").
+    mine, theirs = run(0.05 * nrm)
     worst = max(relerr(m, t) for m, t in zip(mine, theirs))
     assert worst < TOL, worst
+    # (2) SURVEY 8(d)'s lamda = 1e-2*||A^H A||_2: here the complex64 oracle drifts 2e-4 from the
+    # fp64 recurrence mid-run, so 1e-5 iterate-by-iterate is below the oracle's own noise floor;
+    # the meaningful bar is "no further from the fp64 truth than the oracle is".
+    lam = 1e-2 * nrm
+    mine, theirs = run(lam)
+    truth = osense.SenseTruth64(ref).cg(b, lam, 50)
+    for k, (m, t, tr) in enumerate(zip(mine, theirs, truth)):
+        assert relerr(m, tr) <= max(TOL, 3 * relerr(t, tr)), (k, relerr(m, tr), relerr(t, tr))
+    assert relerr(mine[-1], truth[-1]) < TOL
+
+
+@pytest.mark.parametrize("name", ["sense_small", "sense_odd"])
+def test_device_built_operator_matches_reference(B, golden_dir, name):
+    """G' and P^H built by CUDA kernels from (coord, maps): CSR structure bit-identical to the
+    reference's, values bit-identical (no aliasing taps in these grids), applies within 1e-5."""
+    from indigo_b200.sense import sense_operator_device
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    N = tuple(int(v) for v in g["N"])
+    A = sense_operator_device(B, N, g["coord"], g["maps"], float(g["oversamp"]))
+    Gd, Pd = leaves(A)
+    for d, tag in ((Gd, "G"), (Pd, "P")):
+        assert d.shape == tuple(g[tag + "_shape"])
+        np.testing.assert_array_equal(d.rowPtrs.to_host(), g[tag + "_indptr"])
+        np.testing.assert_array_equal(d.colInds.to_host(), g[tag + "_indices"])
+        np.testing.assert_array_equal(d.values.to_host(), g[tag + "_data"])
+        assert d._exwrite == int(g[tag + "_exwrite"])
+    assert relerr(A * g["x"], g["Ax"]) < TOL
+    assert relerr(A.H * g["y"], g["AHy"]) < TOL
+    assert relerr(normal_operator(A) * g["x"], g["AHAx"]) < TOL
+    Aw = sense_operator_device(B, N, g["coord"], g["maps"], float(g["oversamp"]), weights=g["cg_w"])
+    x = np.zeros_like(g["cg_b"], order='F')
+    B.cg(normal_operator(Aw), g["cg_b"], x, lamda=float(g["cg_lamda"]), maxiter=len(g["cg_iterates"]), tol=0.0)
+    assert relerr(x, g["cg_iterates"][-1]) < TOL
+
+
+def test_device_built_cfg1_structure(B, golden_dir):
+    """Config 1 has a 2-point z axis: 5-6 taps alias onto 2 cells and are merged."""
+    from indigo_b200.sense import sense_operator_device
+    g = np.load(os.path.join(golden_dir, "sense_cfg1_digest.npz"))
+    N, C = tuple(int(v) for v in g["N"]), int(g["C"])
+    rs = np.random.RandomState(int(g["seed"]))
+    maps = synth.unit_rss_maps(rs, N, C)
+    A = sense_operator_device(B, N, synth.radial_2d(402, 512), maps, float(g["oversamp"]))
+    Gd, Pd = leaves(A)
+    assert Gd.nnz == int(g["G_nnz"]) and Pd.nnz == int(g["P_nnz"])
+    assert sha(Gd.rowPtrs.to_host()) == str(g["G_indptr_sha"]) and sha(Gd.colInds.to_host()) == str(g["G_indices_sha"])
+    assert sha(Pd.rowPtrs.to_host()) == str(g["P_indptr_sha"]) and sha(Pd.colInds.to_host()) == str(g["P_indices_sha"])
+    sub = slice(None, None, 997)
+    assert relerr(Gd.values.to_host()[sub], g["G_data_sub"]) < 1e-6
+    np.testing.assert_array_equal(Pd.values.to_host()[sub], g["P_data_sub"])
+    x = synth.rand64c(rs, int(np.prod(N)), 1)
+    assert relerr((normal_operator(A) * x).ravel(order='F')[sub], g["AHAx_sub"]) < TOL
