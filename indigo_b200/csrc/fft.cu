@@ -18,6 +18,7 @@
 // the CPU emulation harness used by the GPU-less tests).
 #include "fft_plan.hpp"
 
+#include <cstdlib>
 #include <new>
 
 namespace ib200 {
@@ -28,6 +29,53 @@ template <bool AXIS0>
 __global__ void __launch_bounds__(kFftThreads) fft_pass_kernel(const FftKernelArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     fft_pass_body<AXIS0>(a, reinterpret_cast<c64 *>(smem_raw), (int64_t)blockIdx.x, (int)threadIdx.x, (int)blockDim.x);
+}
+
+template <int N, int R0, int R1, int R2, bool AXIS0, int THREADS>
+__global__ void __launch_bounds__(THREADS, (THREADS > 256 ? 2 : 2)) fft_spec_kernel(const FftKernelArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    fft_pass_body_spec<N, R0, R1, R2, AXIS0>(a, reinterpret_cast<c64 *>(smem_raw), (int64_t)blockIdx.x,
+                                             (int)threadIdx.x, (int)blockDim.x);
+}
+
+template <int N, int R0, int R1, int R2, bool AXIS0, int THREADS>
+static int launch_spec_t(cudaStream_t s, const FftKernelArgs &k) {
+    static bool attr_done[64] = {false};
+    const size_t smem = (size_t)(R2 > 1 ? 2 : 1) * N * kSpecLP * sizeof(c64);
+    int dev = 0;
+    IB200_TRY(cudaGetDevice(&dev));
+    if (!attr_done[dev & 63]) {
+        IB200_TRY(cudaFuncSetAttribute(fft_spec_kernel<N, R0, R1, R2, AXIS0, THREADS>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[dev & 63] = true;
+    }
+    const int64_t blocks = AXIS0 ? ceil_div(k.outer, kSpecL) : ceil_div(k.inner, kSpecL) * k.outer;
+    IB200_REQUIRE(blocks < (1LL << 31), "fft: too many tiles for one launch");
+    fft_spec_kernel<N, R0, R1, R2, AXIS0, THREADS><<<(unsigned)blocks, THREADS, smem, s>>>(k);
+    IB200_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int N, int R0, int R1, int R2, bool AXIS0>
+static int launch_spec(cudaStream_t s, const FftKernelArgs &k) {
+    static const int threads = getenv("IB200_FFT_THREADS") ? atoi(getenv("IB200_FFT_THREADS")) : 256;
+    if (threads == 512) return launch_spec_t<N, R0, R1, R2, AXIS0, 512>(s, k);
+    if (threads == 128) return launch_spec_t<N, R0, R1, R2, AXIS0, 128>(s, k);
+    return launch_spec_t<N, R0, R1, R2, AXIS0, 256>(s, k);
+}
+
+// returns 1 if a specialised kernel was launched, 0 if none applies, <0 / >0 on error (offset by 1000)
+static int try_spec(cudaStream_t s, bool axis0, const FftKernelArgs &k) {
+    if (!axis0 && k.inner < kSpecL) return 0;
+    if (axis0 && k.outer < kSpecL) return 0;
+#define IB200_TRY_SPEC(n, r0, r1, r2)                                                        \
+    if (fft_spec_matches(k, n, r0, r1, r2)) {                                                \
+        const int rc = axis0 ? launch_spec<n, r0, r1, r2, true>(s, k) : launch_spec<n, r0, r1, r2, false>(s, k); \
+        return rc == 0 ? 1 : (rc > 0 ? rc + 1000 : rc);                                      \
+    }
+    IB200_FFT_SPEC_LIST(IB200_TRY_SPEC)
+#undef IB200_TRY_SPEC
+    return 0;
 }
 
 }  // namespace ib200
@@ -65,7 +113,13 @@ static int exec_impl(FftPlanData *pl, cudaStream_t s, c64 *y, const c64 *x, int 
     int rc = ensure_device_state(pl);
     if (rc) return rc;
     bool copy_only = false;
+    static const bool use_spec = getenv("IB200_FFT_GENERIC") == nullptr;
     auto launch = [&](bool axis0, int64_t blocks, size_t smem, const FftKernelArgs &k) -> int {
+        if (use_spec) {
+            const int sp = try_spec(s, axis0, k);
+            if (sp == 1) return 0;
+            if (sp != 0) return sp > 1000 ? sp - 1000 : sp;
+        }
         if (axis0) fft_pass_kernel<true><<<(unsigned)blocks, kFftThreads, smem, s>>>(k);
         else       fft_pass_kernel<false><<<(unsigned)blocks, kFftThreads, smem, s>>>(k);
         IB200_LAUNCH_CHECK();

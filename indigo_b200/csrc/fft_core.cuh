@@ -359,4 +359,163 @@ IB_HD void fft_pass_body(const FftKernelArgs &a, c64 *bufA, int64_t block, int t
         for (int i = tid; i < copy_items; i += nt) fft_store_item(c, src, AXIS0, i);
 }
 
+
+// ============================================================================
+// Compile-time specialised passes for the grid sizes MRI reconstructions use.
+// Same Stockham recurrence as above, but n, the radix sequence, p and t are
+// template constants (no integer division or runtime radix dispatch), twiddle
+// powers come from one table load per butterfly by log-depth multiplication,
+// tiles are always L = 16 lines, and on axis 0 the first and last stage talk to
+// global memory directly with positions as the fast thread index (coalesced)
+// instead of transposing through an extra shared-memory round trip.
+// ============================================================================
+static const int kSpecL = 16, kSpecLP = 17;
+
+// powers w^1 .. w^(R-1) with multiplication depth log2(R)
+template <int R>
+IB_HD void twiddle_powers(c64 w, c64 (&pw)[R]) {
+    pw[0] = h_mk(1.f, 0.f);
+    if (R > 1) pw[1] = w;
+#pragma unroll
+    for (int s = 2; s < R; ++s) pw[s] = h_mul(pw[s / 2], pw[s - s / 2]);
+}
+
+// shared-memory address of (position, line); ROT_R > 0 rotates the line index by
+// pos / ROT_R so that a position-fast writer with an even radix stays conflict free
+template <int ROT_R>
+IB_HD int spec_addr(int pos, int l) {
+    if (ROT_R > 0) return pos * kSpecLP + ((l + pos / ROT_R) & (kSpecL - 1));
+    return pos * kSpecLP + l;
+}
+
+// lines-fast stage (strided axes: every stage; axis 0: the middle stage)
+template <int N, int R, int P, bool SRC_G, bool DST_G, int ROT_IN, int ROT_OUT>
+IB_HD void spec_stage_lfast(const FftCtx &c, const c64 *sin_, c64 *sout, int tid, int nt) {
+    constexpr int T = N / R, ITEMS = kSpecL * T, STEP = N / (P * R);
+    for (int idx = tid; idx < ITEMS; idx += nt) {
+        const int l = idx & (kSpecL - 1), b = idx >> 4;
+        if (l >= c.nl) continue;
+        const int k = P == 1 ? 0 : b % P;
+        c64 u[R];
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+            const int pos = b + s * T;
+            u[s] = SRC_G ? fft_gload(c, l, pos) : sin_[spec_addr<ROT_IN>(pos, l)];
+        }
+        if (P > 1) {
+            c64 pw[R];
+            twiddle_powers<R>(c.tw[k * STEP], pw);
+#pragma unroll
+            for (int s = 1; s < R; ++s) u[s] = h_mul(u[s], pw[s]);
+        }
+        Dft<R>::run(u);
+        const int o0 = (b - k) * R + k;
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            const int pos = o0 + q * P;
+            if (DST_G) fft_gstore(c, l, pos, u[q]);
+            else sout[spec_addr<ROT_OUT>(pos, l)] = u[q];
+        }
+    }
+}
+
+// axis 0, first stage (P = 1): global -> shared, positions fast
+template <int N, int R, int ROT_OUT>
+IB_HD void spec_stage_first_bfast(const FftCtx &c, c64 *sout, int tid, int nt) {
+    constexpr int T = N / R, ITEMS = kSpecL * T;
+    for (int idx = tid; idx < ITEMS; idx += nt) {
+        const int b = idx % T, l = idx / T;
+        if (l >= c.nl) continue;
+        c64 u[R];
+#pragma unroll
+        for (int s = 0; s < R; ++s) u[s] = fft_gload(c, l, b + s * T);
+        Dft<R>::run(u);
+#pragma unroll
+        for (int q = 0; q < R; ++q) sout[spec_addr<ROT_OUT>(b * R + q, l)] = u[q];
+    }
+}
+
+// axis 0, last stage (P = N / R): shared -> global, positions fast
+template <int N, int R, int ROT_IN>
+IB_HD void spec_stage_last_bfast(const FftCtx &c, const c64 *sin_, int tid, int nt) {
+    constexpr int T = N / R, ITEMS = kSpecL * T;
+    for (int idx = tid; idx < ITEMS; idx += nt) {
+        const int b = idx % T, l = idx / T;
+        if (l >= c.nl) continue;
+        c64 u[R], pw[R];
+#pragma unroll
+        for (int s = 0; s < R; ++s) u[s] = sin_[spec_addr<ROT_IN>(b + s * T, l)];
+        twiddle_powers<R>(c.tw[b], pw);                 // k = b, step = 1
+#pragma unroll
+        for (int s = 1; s < R; ++s) u[s] = h_mul(u[s], pw[s]);
+        Dft<R>::run(u);
+#pragma unroll
+        for (int q = 0; q < R; ++q) fft_gstore(c, l, b + q * T, u[q]);
+    }
+}
+
+template <int N, int R0, int R1, int R2, bool AXIS0>
+IB_HD void fft_pass_body_spec(const FftKernelArgs &a, c64 *bufA, int64_t block, int tid, int nt) {
+    constexpr bool THREE = R2 > 1;
+    FftCtx c;
+    c.n = N; c.L = kSpecL; c.log2L = 4; c.LP = kSpecLP;
+    c.tw = a.tw;
+    c.swap_in = a.swap_in; c.swap_out = a.swap_out; c.conj_in = a.conj_in; c.conj_out = a.conj_out;
+    c64 *bufB = bufA + (size_t)N * kSpecLP;
+    int64_t base;
+    if (AXIS0) {
+        const int64_t line0 = block * kSpecL, left = a.outer - line0;
+        c.nl = left < kSpecL ? (int)left : kSpecL;
+        base = line0 * N;
+        c.gstride_j = 1; c.gstride_l = N;
+    } else {
+        const int64_t tiles = (a.inner + kSpecL - 1) / kSpecL;
+        const int64_t o = block / tiles, s0 = (block % tiles) * kSpecL, left = a.inner - s0;
+        c.nl = left < kSpecL ? (int)left : kSpecL;
+        base = o * N * a.inner + s0;
+        c.gstride_j = a.inner; c.gstride_l = 1;
+    }
+    c.gin = a.x + base; c.gout = a.y + base;
+    const int64_t dbase = a.plane > 0 ? base % a.plane : 0;
+    c.din = a.din ? a.din + dbase : nullptr;
+    c.dout = a.dout ? a.dout + dbase : nullptr;
+
+    if (AXIS0) {
+        constexpr int ROT = (R0 % 2 == 0) ? R0 : 0;
+        spec_stage_first_bfast<N, R0, ROT>(c, bufA, tid, nt);
+        IB_SYNC();
+        if (THREE) {
+            spec_stage_lfast<N, R1, R0, false, false, ROT, 0>(c, bufA, bufB, tid, nt);
+            IB_SYNC();
+            spec_stage_last_bfast<N, THREE ? R2 : R1, 0>(c, bufB, tid, nt);
+        } else {
+            spec_stage_last_bfast<N, R1, ROT>(c, bufA, tid, nt);
+        }
+    } else {
+        spec_stage_lfast<N, R0, 1, true, false, 0, 0>(c, nullptr, bufA, tid, nt);
+        IB_SYNC();
+        if (THREE) {
+            spec_stage_lfast<N, R1, R0, false, false, 0, 0>(c, bufA, bufB, tid, nt);
+            IB_SYNC();
+            spec_stage_lfast<N, THREE ? R2 : R1, R0 * R1, false, true, 0, 0>(c, bufB, nullptr, tid, nt);
+        } else {
+            spec_stage_lfast<N, R1, R0, false, true, 0, 0>(c, bufA, nullptr, tid, nt);
+        }
+    }
+}
+
+// sizes with a specialised pass: X(n, r0, r1, r2)   (r2 == 1: two stages).
+// The radix order must be the planner's (fft_factorize).
+#define IB200_FFT_SPEC_LIST(X) \
+    X(32, 8, 4, 1) X(52, 13, 4, 1) X(64, 8, 8, 1) X(104, 13, 8, 1) X(128, 16, 8, 1) X(192, 3, 8, 8) \
+    X(208, 13, 16, 1) X(256, 16, 16, 1) X(320, 5, 8, 8) X(384, 3, 16, 8) X(416, 13, 8, 4) X(448, 7, 8, 8) \
+    X(512, 8, 8, 8) X(640, 5, 16, 8) X(768, 3, 16, 16) X(832, 13, 8, 8) X(1024, 16, 8, 8)
+
+IB_HD bool fft_spec_matches(const FftKernelArgs &a, int n, int r0, int r1, int r2) {
+    const int nst = r2 > 1 ? 3 : 2;
+    if (a.n != n || a.st.nst != nst) return false;
+    if (a.st.radix[0] != r0 || a.st.radix[1] != r1) return false;
+    return nst == 2 || a.st.radix[2] == r2;
+}
+
 }  // namespace ib200

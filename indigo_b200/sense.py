@@ -55,6 +55,14 @@ def normal_operator(A):
     in as a Sum: under coil sharding a Sum would add it once per rank."""
     AHA = A.H * A
     AHA._name = 'SENSE'
+    # The arena reserved by A.optimize() is sized for A alone (transforms.py:72-76); A^H A nests one
+    # more Product temporary (the k-space vector).  The reference gets away with it because its
+    # estimate also counts the matrices' bytes; size the arena for the tree that is evaluated.
+    B = A._backend
+    need = int(AHA.memusage()) // _C64.itemsize
+    if getattr(B, '_scratch', None) is not None and B._scratch.size < need and B._scratch_pos == 0:
+        B._scratch = None
+        B._scratch = B.empty_array((need,), _C64)
     return AHA
 
 
@@ -189,6 +197,7 @@ def sense_operator_device(B, N, coord, maps, oversamp=2.0, weights=None, width=3
         def _get_or_create_device_matrix(self):
             return self._matrix_d
 
+    _DevSp.__name__ = 'SpMatrix'          # tree visitors dispatch on the class name
     Gn = _DevSp(B, Gd, 'interp*mod*scale')
     Pn = _DevSp(B, Pd, '((x)mod*zpad*apod)*+.H')
     F = B.UnscaledFFT(oN, _C64, name='fft')

@@ -7,6 +7,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 namespace ib200 {
@@ -23,6 +24,7 @@ extern "C" const char *emul_last_error() { return g_err; }
 
 extern "C" int emul_fft(int ndim, const int64_t *dims, int64_t batch, float *y, const float *x, int direction,
                         const float *din, int conj_in, const float *dout, int conj_out, int *tile_L_out) {
+    const bool use_spec = getenv("IB200_FFT_GENERIC") == nullptr;
     FftPlanData pl;
     int rc = fft_plan_init(&pl, ndim, dims, batch);
     if (rc) return rc;
@@ -35,6 +37,22 @@ extern "C" int emul_fft(int ndim, const int64_t *dims, int64_t batch, float *y, 
         std::vector<c64> sm(smem / sizeof(c64) + 1);
         if (tile_L_out) tile_L_out[pass] = k.L;
         ++pass;
+        bool spec = false;
+        if (use_spec && (axis0 ? k.outer >= kSpecL : k.inner >= kSpecL)) {
+#define EMUL_SPEC(n, r0, r1, r2)                                                                   \
+            if (!spec && fft_spec_matches(k, n, r0, r1, r2)) {                                     \
+                spec = true;                                                                       \
+                std::vector<c64> sp((size_t)2 * n * kSpecLP + 1);                                  \
+                const int64_t nb = axis0 ? ceil_div(k.outer, kSpecL) : ceil_div(k.inner, kSpecL) * k.outer; \
+                for (int64_t b = 0; b < nb; ++b) {                                                 \
+                    if (axis0) fft_pass_body_spec<n, r0, r1, r2, true>(k, sp.data(), b, 0, 1);     \
+                    else       fft_pass_body_spec<n, r0, r1, r2, false>(k, sp.data(), b, 0, 1);    \
+                }                                                                                  \
+            }
+            IB200_FFT_SPEC_LIST(EMUL_SPEC)
+#undef EMUL_SPEC
+        }
+        if (spec) { if (tile_L_out) tile_L_out[pass - 1] = -16; return 0; }
         for (int64_t b = 0; b < blocks; ++b) {
             if (axis0) fft_pass_body<true>(k, sm.data(), b, 0, 1);
             else       fft_pass_body<false>(k, sm.data(), b, 0, 1);

@@ -14,7 +14,8 @@ from indigo_b200 import B200Backend, synth        # noqa: E402
 C64 = np.dtype('complex64')
 B = B200Backend(0)
 lib = B._lib
-PEAK = json.load(open('MEASURED_PEAKS.json'))['hbm_gbs'] if len(sys.argv) < 2 else float(sys.argv[1])
+PEAK = json.load(open('MEASURED_PEAKS.json'))['hbm_gbs']
+MODE = sys.argv[1] if len(sys.argv) > 1 else "all"
 
 
 def timeit(fn, reps=5, warm=2):
@@ -100,6 +101,12 @@ def csr_probe(grid, nspokes, nread, ncols):
 
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0), "peak", PEAK)
+    if MODE == "fft":          # short run for ncu
+        fft_probe((416, 416, 416, 4))
+        sys.exit(0)
+    if MODE == "csr":
+        csr_probe((416, 416, 416), 2048, 416, 16)
+        sys.exit(0)
     blas_probe(8998912)
     blas_probe(1 << 26)
     fft_probe((512, 512, 2, 8))
