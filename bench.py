@@ -103,20 +103,51 @@ class ClockSampler(object):
 
 # --------------------------------------------------------------------------- ours
 def algorithmic_bytes(call):
-    """each operand counted once."""
+    """each operand counted once.  The fused steps are charged the
+    compulsory traffic of the fused formulation (pruned passes), not of the calls they replace."""
     if call["op"] == "ccsrmm":
         b = call["nnz"] * 12 + (call["m"] + 1) * 4 + 8 * call["ncols"] * (call["k"] + call["m"])
         return b + (8 * call["ncols"] * (call["k"] if call["adjoint"] else call["m"]) if call["beta_nz"] else 0)
+    if call["op"] == "fused_fft":
+        N, oN, C = call["N"], call["oN"], call["C"]
+        nvox = N[0] * N[1] * N[2]
+        px = oN[0] * N[1] * N[2]                 # points after the x pass
+        py = oN[0] * oN[1] * N[2]                # after the y pass
+        pz = oN[0] * oN[1] * oN[2]
+        # image + pf, then (read + write) of each of the three pruned passes
+        return 8 * nvox + 8 * nvox * C + 8 * C * (px + (px + py) + (py + pz))
     return 16 * call["points"]
 
 
 class CallTimer(object):
-    """Brackets every Backend call of the apply with CUDA events on the launching stream."""
+    """Brackets every Backend call (or fused step) of the apply with CUDA events on the launching stream."""
 
-    def __init__(self, B, torch):
+    def __init__(self, B, torch, dev=None):
         self.B, self.torch, self.records, self.on = B, torch, [], False
         for name in ("ccsrmm", "fftn", "ifftn"):
             setattr(B, name, self._wrap(name, getattr(B, name)))
+        if dev is not None:
+            fft = dict(op="fused_fft", N=dev.N, oN=dev.oN, C=dev.C)
+            gfw = dict(op="ccsrmm", m=dev.M, k=dev.on, nnz=dev.nnz, ncols=dev.C, adjoint=False, beta_nz=False)
+            gad = dict(op="ccsrmm", m=dev.on, k=dev.M, nnz=dev.nnz, ncols=dev.C, adjoint=False, beta_nz=False)
+            shp = "x".join(str(v) for v in dev.oN)
+            for name, key, info in (
+                    ("expand_fft", "expand_fft[pf.*x -> zpad -> FFT3 %s x%d coils, pruned]" % (shp, dev.C), fft),
+                    ("grid_to_samples", "ccsrmm_il[G' %dx%d nnz/row=%.0f ncols=%d]" % (dev.M, dev.on, dev.nnz / dev.M, dev.C), gfw),
+                    ("samples_to_grid", "ccsrmm_il[G'^H stored %dx%d nnz/row=%.0f ncols=%d]" % (dev.on, dev.M, dev.nnz / dev.on, dev.C), gad),
+                    ("ifft_combine", "ifft_combine[IFFT3 %s x%d coils -> crop -> sum_c conj(pf), pruned]" % (shp, dev.C), fft)):
+                setattr(dev, name, self._wrap_fused(key, info, getattr(dev, name)))
+
+    def _wrap_fused(self, key, info, fn):
+        def timed(*a, **k):
+            if not self.on:
+                return fn(*a, **k)
+            e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+            n0 = self.B._lib.launch_count()
+            e0.record(); out = fn(*a, **k); e1.record()
+            self.records.append((key, info, e0, e1, self.B._lib.launch_count() - n0))
+            return out
+        return timed
 
     def _wrap(self, name, fn):
         def timed(*a, **k):
@@ -163,6 +194,7 @@ def run_ours(args):
     import torch.distributed as dist
     from indigo_b200 import B200Backend, synth
     from indigo_b200.sense import sense_operator_device, normal_operator
+    from indigo_b200.fused import sense_operator_fused
     from indigo_b200.team import CoilTeam, coil_slice
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -182,14 +214,25 @@ def run_ours(args):
     maps = synth.unit_rss_maps(rs, N, C)
     mine = coil_slice(C, rank, world)
     t0 = time.time()
-    A = sense_operator_device(B, N, coord, np.asfortranarray(maps[..., mine]), wl["oversamp"])
+    my_maps = np.asfortranarray(maps[..., mine])
+    tree = args.tree
+    A = None
+    if tree == "fused":
+        try:
+            A = sense_operator_fused(B, N, coord, my_maps, wl["oversamp"])
+        except RuntimeError as e:                       # grid without specialised passes (e.g. cfg1's 512x512x2)
+            print("fused path unavailable (%s); using the six-call tree" % e, file=sys.stderr)
+            tree = "o3"
+    if A is None:
+        A = sense_operator_device(B, N, coord, my_maps, wl["oversamp"])
     AHA = normal_operator(A)
+    B.barrier()
     setup_s = time.time() - t0
     nvox = int(np.prod(N))
     x_h = B.pinned_array((nvox, 1)); x_h[...] = synth.rand64c(rs, nvox, 1)
     y_h = B.pinned_array((nvox, 1))
     x_d = B.copy_array(np.asarray(x_h)); y_d = B.zero_array((nvox, 1), C64)
-    timer = CallTimer(B, torch)
+    timer = CallTimer(B, torch, getattr(A, '_dev', None))
     lib = B._lib
 
     def apply():
@@ -245,7 +288,10 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "complex64 (fp32 accumulate)",
             "data": "synthetic (seeded kooshball trajectory, rand64c image and unit-RSS coil maps)",
-            "config": {"workload": wl["desc"], "tree": "-O3 (examples/pics.py recipe), device-built CSR operands",
+            "config": {"workload": wl["desc"],
+                       "tree": ("fused B200 recipe: expand+FFT (pruned, coil-interleaved) -> G' gather -> stored G'^H gather -> "
+                                "IFFT+combine; 4 fused steps replace the six calls of the -O3 tree" if tree == "fused" else
+                                "-O3 (examples/pics.py recipe), device-built CSR operands, six Backend calls"),
                        "parallelism": "coil-sharded x%d, NCCL all-reduce of the image" % world if world > 1 else "single GPU",
                        "l2": "no explicit flush: every call streams operands far larger than L2 (grid %.1f GB)" %
                              (8.0 * np.prod([int(n * wl["oversamp"]) for n in N]) * C / world / 1e9)},
@@ -356,6 +402,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tree", default="fused", choices=["fused", "o3"],
+                    help="fused: backend-specific fused recipe (default); o3: the reference's six-call -O3 tree")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -99,6 +99,30 @@ int ib200_cg_p(void *stream, int64_t n, void *p, const void *r, double *scal);
 int ib200_ccsrmm(void *stream, int adjoint, int exwrite, int64_t m, int64_t k, int64_t ncols, int64_t nnz,
                  float alpha_re, float alpha_im, const void *vals, const int32_t *colind, const int32_t *rowptr,
                  const void *X, int64_t ldx, float beta_re, float beta_im, void *Y, int64_t ldy);
+/* Coil-interleaved fast path of Backend.ccsrmm for 2..32 right-hand-side columns
+ * (same reference interface: backend.py:514-519; the layout conversion replaces
+ * the strided per-coil gathers the column-major interface would force).
+ *   ib200_interleave   : Xil[r*pitch + c] = X[r + c*ldx]
+ *   ib200_ccsrmm_il    : Yil[r*ypitch + c] = alpha * sum_p vals[p] * Xil[colind[p]*xpitch + c]
+ *   ib200_deinterleave : Y[r + c*ldy] = Yil[r*pitch + c] + beta * Y[r + c*ldy]
+ * The adjoint product uses the same entry on the stored conjugate transpose
+ * (ib200_csr_transpose_conj), so neither direction needs atomics. */
+int ib200_interleave(void *stream, int64_t rows, int64_t ncols, const void *X, int64_t ldx, void *Xil, int64_t pitch);
+int ib200_deinterleave(void *stream, int64_t rows, int64_t ncols, const void *Yil, int64_t pitch,
+                       float beta_re, float beta_im, void *Y, int64_t ldy);
+int ib200_ccsrmm_il(void *stream, int64_t m, int64_t k, int64_t ncols, int64_t nnz, float alpha_re, float alpha_im,
+                    const void *vals, const int32_t *colind, const int32_t *rowptr,
+                    const void *Xil, int64_t xpitch, void *Yil, int64_t ypitch,
+                    const int32_t *rowmap, int rows_per_group);
+/* rowmap (optional, m int32): row r of the matrix is written to output row rowmap[r]; negative
+ * entries are padding rows and write nothing.  rows_per_group: consecutive-row blocking factor of
+ * the kernel (0 = automatic).  Both exist for matrices whose rows were stored in tile-major
+ * order of a 3-D grid so that the rows one CTA owns share their operands:
+ * ib200_grid_tile_rank fills colrank[g] = padded tile-major rank of grid point g (x fastest)
+ * and rowmap[rank] = g (or -1 for padding); *padded_rows = number of ranks.  Pass NULL for both
+ * arrays to query the size only. */
+int ib200_grid_tile_rank(void *stream, const int64_t grid[3], const int64_t tile[3], int32_t *colrank, int32_t *rowmap,
+                         int64_t *padded_rows);
 /* The inspector of _customcpu.c:179-215 on the device: out = {rows with >=1
  * entry, columns with >=1 entry, exwrite flag, max entries in one column}.
  * `work` is k int32 of device scratch.  Synchronises `stream`. */
@@ -107,10 +131,14 @@ int ib200_csr_inspect(void *stream, int64_t m, int64_t k, const int32_t *colind,
 /* Device-side conjugate transpose of a CSR matrix (the "stored adjoint" used
  * for non-exclusive-write adjoints).  t_rowptr[k+1], t_colind[nnz], t_vals[nnz]
  * are caller-allocated device buffers; `work` is k+1 int32 of device scratch.
- * Output rows are sorted by column.  Synchronises `stream`. */
+ * Output rows are sorted by column.  `colrank` (optional, k int32, a permutation
+ * of 0..k-1) places the transposed row of column c at position colrank[c], so
+ * that rows which are neighbours on a 3-D grid can be stored next to each other
+ * (see ib200_grid_tile_rank); NULL keeps the natural order.  Synchronises `stream`. */
 int ib200_csr_transpose_conj(void *stream, int64_t m, int64_t k, int64_t nnz,
                              const void *vals, const int32_t *colind, const int32_t *rowptr,
-                             void *t_vals, int32_t *t_colind, int32_t *t_rowptr, int32_t *work);
+                             void *t_vals, int32_t *t_colind, int32_t *t_rowptr, int32_t *work,
+                             const int32_t *colrank);
 /* Backend.cdiamm, backend.py:521-526 (oracle np.py:129-136; _customgpu.cu:83-143).
  * A is m x k in DIA form; data is (ncolsA x noffsets) column-major where
  * ncolsA = k, i.e. scipy's dia.data transposed (backend.py:610).
@@ -147,6 +175,28 @@ int ib200_fft_exec(ib200_fft_plan plan, void *stream, void *y, const void *x, in
  * broadcast over the batch; conj_* conjugates the diagonal. */
 int ib200_fft_exec_diag(ib200_fft_plan plan, void *stream, void *y, const void *x, int direction,
                         const void *d_in, int conj_in, const void *d_out, int conj_out);
+
+/* ------------------------------------------------------------------ fused SENSE transforms
+ * Backend-specific fusion of the first two and last two calls of the -O3 SENSE apply
+ * (SURVEY.md section 3.1):   ccsrmm(P^H, adjoint) -> fftn     and     ifftn -> ccsrmm(P^H),
+ * P = kron(I_C, mod*zpad*apod) * vstack(maps) (examples/pics.py:111-126, indigo/backends/
+ * backend.py:355-387).  The oversampled grid is kept coil-interleaved, grid[z][y][x][coil],
+ * which is the layout ib200_ccsrmm_il gathers from; `pf` is the dense factor
+ * pf[voxel*C + coil] = (mod*apod)[voxel] * maps[voxel, coil].  Zero-padding and cropping are
+ * the input/output windows of the passes, so the zero rows of the padded volume are never
+ * written, read or transformed before the pass that fills them.
+ *   expand_fft   : grid = FFT3( zpad( pf .* img ) )                      (unscaled forward)
+ *   ifft_combine : img  = alpha * sum_c conj(pf) .* crop( IFFT3(grid) ) + beta * img
+ *                  (unscaled inverse; grid is overwritten; beta == 0 never reads img)
+ * Grid extents must have a specialised FFT (32, 52, 64, 104, 128, 192, 208, 256, 320, 384, 416,
+ * 448, 512, 640, 768, 832, 1024); otherwise plan creation returns IB200_E_UNSUPPORTED and the
+ * caller stays on the six-call path. */
+typedef struct ib200_sense_plan_s *ib200_sense_plan;
+int ib200_sense_plan_create(ib200_sense_plan *plan, const int64_t N[3], const int64_t oN[3], int64_t ncoils);
+int ib200_sense_plan_destroy(ib200_sense_plan plan);
+int ib200_sense_expand_fft(ib200_sense_plan plan, void *stream, void *grid_il, const void *img, const void *pf);
+int ib200_sense_ifft_combine(ib200_sense_plan plan, void *stream, void *img_out, void *grid_il, const void *pf,
+                             float alpha_re, float alpha_im, float beta_re, float beta_im);
 
 /* ------------------------------------------------------------------ operator construction on the device
  * Setup-time replacements for the host construction of the two sparse factors

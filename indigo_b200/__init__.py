@@ -8,7 +8,8 @@ indigo_b200 -- B200 (sm_100a) execution backend for indigo's `Backend` interface
 Importing this package does not touch CUDA; the shared library is loaded (and
 its absence reported, loudly) when a backend is constructed.
 """
-__all__ = ["B200Backend", "get_backend", "register", "sense_operator", "normal_operator", "CoilTeam"]
+__all__ = ["B200Backend", "get_backend", "register", "sense_operator", "sense_operator_fused", "normal_operator",
+           "CoilTeam"]
 
 
 def __getattr__(name):
@@ -18,6 +19,9 @@ def __getattr__(name):
     if name in ("sense_operator", "normal_operator", "sqrt_dcf"):
         from . import sense
         return getattr(sense, name)
+    if name == "sense_operator_fused":
+        from .fused import sense_operator_fused
+        return sense_operator_fused
     if name == "CoilTeam":
         from .team import CoilTeam
         return CoilTeam

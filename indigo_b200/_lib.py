@@ -34,8 +34,12 @@ SIGNATURES = {
     "ib200_cg_xr": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "ib200_cg_p": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "ib200_ccsrmm": (_i, [_vp, _i, _i, _i64, _i64, _i64, _i64, _f, _f, _vp, _vp, _vp, _vp, _i64, _f, _f, _vp, _i64]),
+    "ib200_interleave": (_i, [_vp, _i64, _i64, _vp, _i64, _vp, _i64]),
+    "ib200_deinterleave": (_i, [_vp, _i64, _i64, _vp, _i64, _f, _f, _vp, _i64]),
+    "ib200_ccsrmm_il": (_i, [_vp, _i64, _i64, _i64, _i64, _f, _f, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i]),
+    "ib200_grid_tile_rank": (_i, [_vp, POINTER(_i64), POINTER(_i64), _vp, _vp, POINTER(_i64)]),
     "ib200_csr_inspect": (_i, [_vp, _i64, _i64, _vp, _vp, _vp, POINTER(_i64)]),
-    "ib200_csr_transpose_conj": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ib200_csr_transpose_conj": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ib200_kb_count": (_i, [_vp, _i64, _vp, POINTER(_i64), c_double, _vp]),
     "ib200_exclusive_scan_i32": (_i, [_vp, _i64, _vp, _vp]),
     "ib200_kb_fill": (_i, [_vp, _i64, _vp, POINTER(_i64), c_double, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
@@ -49,6 +53,10 @@ SIGNATURES = {
     "ib200_fft_plan_describe": (_i, [_vp, _i, POINTER(_i), _i]),
     "ib200_fft_exec": (_i, [_vp, _vp, _vp, _vp, _i]),
     "ib200_fft_exec_diag": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i]),
+    "ib200_sense_plan_create": (_i, [POINTER(_vp), POINTER(_i64), POINTER(_i64), _i64]),
+    "ib200_sense_plan_destroy": (_i, [_vp]),
+    "ib200_sense_expand_fft": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "ib200_sense_ifft_combine": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f]),
     "ib200_cgemm": (_i, [_vp, _i, _i64, _i64, _i64, _f, _f, _vp, _i64, _vp, _i64, _f, _f, _vp, _i64]),
     "ib200_csymm": (_i, [_vp, _i, _i64, _i64, _f, _f, _vp, _i64, _vp, _i64, _f, _f, _vp, _i64]),
 }

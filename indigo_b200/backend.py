@@ -202,12 +202,11 @@ def make_backend_class(Base, name="B200Backend"):
                       100 * self._row_frac, 100 * self._col_frac, self._exwrite)
 
         def _use_stored_adjoint(self):
+            # 'auto': always.  With the coil-interleaved gather (csrmm_il.cu) the transposed matrix
+            # costs one full line per stored entry, against one L2 atomic per entry AND coil for the
+            # scatter (measured 44 ms vs 23 ms forward at cfg3 before the re-layout, profiles/r01_s1_*).
             mode = self._backend.stored_adjoints
-            if mode == 'auto':
-                # long rows (gridding stencils): one RED.64 per update beats gathering through a
-                # transposed matrix whose rows are short and whose operand rows are scattered
-                return self.shape[0] > 0 and (int(self.values.size) / self.shape[0]) < 32
-            return bool(mode)
+            return True if mode == 'auto' else bool(mode)
 
         def _stored_adjoint(self):
             if self._adj is None:
@@ -218,7 +217,7 @@ def make_backend_class(Base, name="B200Backend"):
                 t_val = b.empty_array((max(nnz, 1),), _C64, name=self._name + ".H.data")
                 work = b.empty_array((k + 1,), np.dtype('int32'))
                 b._lib.csr_transpose_conj(b._stream, m, k, nnz, self.values.ptr, self.colInds.ptr, self.rowPtrs.ptr,
-                                          t_val.ptr, t_ind.ptr, t_ptr.ptr, work.ptr)
+                                          t_val.ptr, t_ind.ptr, t_ptr.ptr, work.ptr, None)
                 self._adj = (t_ptr, t_ind, t_val)
             return self._adj
 
@@ -237,6 +236,7 @@ def make_backend_class(Base, name="B200Backend"):
         dndarray = B200Array
         csr_matrix = B200Csr
         stored_adjoints = 'auto'        # True / False / 'auto': keep A^H in CSR for non-exclusive-write matrices
+        il_min_work = 1 << 14           # nnz*ncols from which multi-column products take the interleaved path
 
         def __init__(self, device_id=0, lib=None):
             super().__init__(device_id)
@@ -250,6 +250,7 @@ def make_backend_class(Base, name="B200Backend"):
             torch.cuda.set_device(self._device)
             self._plans = {}
             self._cg_scal = None
+            self._il_bufs = {}
 
         # ------------------------------------------------------------ plumbing
         @property
@@ -351,13 +352,35 @@ def make_backend_class(Base, name="B200Backend"):
             self._lib.fft_exec(self._fft_plan(x.shape), self._stream, y.ptr, x.ptr, +1)
 
         # ------------------------------------------------------------ sparse  (backend.py:514-533)
+        def _il_scratch(self, which, nelem):
+            """Backend-owned buffers for the coil-interleaved copies of X and Y (grown on demand,
+            never shrunk; they are not part of indigo's scratch arena)."""
+            buf = self._il_bufs.get(which)
+            if buf is None or buf.numel() < nelem * 8:
+                self._il_bufs[which] = None
+                buf = self._torch.empty(max(nelem, 1) * 8, dtype=self._torch.uint8, device=self._device)
+                self._il_bufs[which] = buf
+            return buf.data_ptr()
+
         def ccsrmm(self, y, A_shape, A_indx, A_ptr, A_vals, x, alpha=1, beta=0, adjoint=False, exwrite=False):
             if A_indx.dtype != np.int32 or A_ptr.dtype != np.int32:
                 raise ValueError("b200 ccsrmm needs int32 indices, got %s" % A_indx.dtype)
             (ar, ai), (br, bi) = _re_im(alpha), _re_im(beta)
             m, k = (int(v) for v in A_shape)
-            self._lib.ccsrmm(self._stream, 1 if adjoint else 0, 1 if exwrite else 0, m, k, int(x.shape[1]),
-                             int(A_vals.size), ar, ai, A_vals.ptr, A_indx.ptr, A_ptr.ptr, x.ptr, x.ld,
+            ncols, nnz = int(x.shape[1]), int(A_vals.size)
+            if (not adjoint and 2 <= ncols <= 32 and m > 0 and k > 0 and nnz * ncols >= self.il_min_work
+                    and (ar != 0.0 or ai != 0.0)):
+                # multi-coil gather: transpose X to [row][coil], gather whole coil segments, transpose back
+                s = self._stream
+                xil = self._il_scratch('x', k * ncols)
+                yil = self._il_scratch('y', m * ncols)
+                self._lib.interleave(s, k, ncols, x.ptr, x.ld, xil, ncols)
+                self._lib.ccsrmm_il(s, m, k, ncols, nnz, ar, ai, A_vals.ptr, A_indx.ptr, A_ptr.ptr, xil, ncols, yil, ncols,
+                                    None, 0)
+                self._lib.deinterleave(s, m, ncols, yil, ncols, br, bi, y.ptr, y.ld)
+                return
+            self._lib.ccsrmm(self._stream, 1 if adjoint else 0, 1 if exwrite else 0, m, k, ncols,
+                             nnz, ar, ai, A_vals.ptr, A_indx.ptr, A_ptr.ptr, x.ptr, x.ld,
                              br, bi, y.ptr, y.ld)
 
         def cdiamm(self, y, shape, offsets, data, x, alpha=1.0, beta=0.0, adjoint=True):

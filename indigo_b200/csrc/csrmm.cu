@@ -19,6 +19,8 @@
 //     the device) and calls the gather kernel instead.
 #include "common.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
+
 namespace ib200 {
 
 // ---------------------------------------------------------------------------
@@ -331,36 +333,43 @@ int exclusive_scan_public(cudaStream_t s, int64_t n, const int32_t *in, int32_t 
     return exclusive_scan(s, n, in, out, out + n);
 }
 
-// unsorted fill: cursor[c] starts at t_rowptr[c]
-__global__ void __launch_bounds__(256) transpose_fill_kernel(int64_t m, const c64 *__restrict__ vals,
-                                                             const int32_t *__restrict__ colind,
-                                                             const int32_t *__restrict__ rowptr, int32_t *cursor,
-                                                             int32_t *__restrict__ tmp_col, c64 *__restrict__ tmp_val) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= m) return;
-    for (int p = rowptr[r]; p < rowptr[r + 1]; ++p) {
-        const int pos = atomicAdd(cursor + colind[p], 1);
-        tmp_col[pos] = (int32_t)r;
-        tmp_val[pos] = cconj(vals[p]);
+// ---- stored adjoint (setup time) ---------------------------------------------
+// rowidx[p] = row that owns stored entry p (one thread per row)
+__global__ void __launch_bounds__(256) expand_rows_kernel(int64_t m, const int32_t *__restrict__ rowptr,
+                                                          int32_t *__restrict__ rowidx) {
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int lane = threadIdx.x & 7;
+    if (row >= m) return;
+    const int p1 = rowptr[row + 1];
+    for (int p = rowptr[row] + lane; p < p1; p += 8) rowidx[p] = (int32_t)row;
+}
+
+__global__ void __launch_bounds__(256) iota_rank_kernel(int64_t nnz, const int32_t *__restrict__ colind,
+                                                        const int32_t *__restrict__ colrank,
+                                                        int32_t *__restrict__ keys, int32_t *__restrict__ pos) {
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += nth) {
+        const int32_t c = colind[p];
+        keys[p] = colrank ? colrank[c] : c;
+        pos[p] = (int32_t)p;
     }
 }
 
-// One warp per output row: rank-sort the (unique) source-row keys of the segment.
-__global__ void __launch_bounds__(256) transpose_sort_kernel(int64_t k, const int32_t *__restrict__ t_rowptr,
-                                                             const int32_t *__restrict__ tmp_col,
-                                                             const c64 *__restrict__ tmp_val,
-                                                             int32_t *__restrict__ t_colind, c64 *__restrict__ t_vals) {
-    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (row >= k) return;
-    const int s0 = t_rowptr[row], s1 = t_rowptr[row + 1];
-    const int len = s1 - s0;
-    for (int i = lane; i < len; i += 32) {
-        const int key = tmp_col[s0 + i];
-        int rank = 0;
-        for (int j = 0; j < len; ++j) rank += tmp_col[s0 + j] < key;
-        t_colind[s0 + rank] = key;
-        t_vals[s0 + rank] = tmp_val[s0 + i];
+// per-column counts of the (ranked) keys
+__global__ void __launch_bounds__(256) count_keys_kernel(int64_t nnz, const int32_t *__restrict__ keys, int32_t *percol) {
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += nth) atomicAdd(percol + keys[p], 1);
+}
+
+__global__ void __launch_bounds__(256) transpose_gather_kernel(int64_t nnz, const int32_t *__restrict__ perm,
+                                                               const int32_t *__restrict__ rowidx,
+                                                               const c64 *__restrict__ vals,
+                                                               int32_t *__restrict__ t_colind, c64 *__restrict__ t_vals) {
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += nth) {
+        const int32_t p = perm[i];
+        t_colind[i] = rowidx[p];
+        t_vals[i] = cconj(vals[p]);
     }
 }
 
@@ -430,7 +439,7 @@ int ib200_csr_inspect(void *stream, int64_t m, int64_t k, const int32_t *colind,
 
 int ib200_csr_transpose_conj(void *stream, int64_t m, int64_t k, int64_t nnz, const void *vals,
                              const int32_t *colind, const int32_t *rowptr, void *t_vals, int32_t *t_colind,
-                             int32_t *t_rowptr, int32_t *work) {
+                             int32_t *t_rowptr, int32_t *work, const int32_t *colrank) {
     IB200_REQUIRE(m >= 0 && k >= 0 && nnz >= 0 && nnz < (1LL << 31), "bad dimensions");
     IB200_REQUIRE(t_rowptr && work, "null pointer");
     cudaStream_t s = as_stream(stream);
@@ -442,27 +451,36 @@ int ib200_csr_transpose_conj(void *stream, int64_t m, int64_t k, int64_t nnz, co
         return 0;
     }
     IB200_REQUIRE(vals && colind && rowptr && t_vals && t_colind, "null pointer");
-    unsigned long long *ctr = nullptr;
-    IB200_TRY(cudaMalloc(&ctr, sizeof(unsigned long long)));
-    cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), s);
-    count_cols_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, s>>>(m, colind, rowptr, work, ctr);
+    // A stable LSD radix sort of the stored entries by (ranked) column keeps the source rows of
+    // every column in ascending order, which is the sorted-index CSR of A^H.
+    int32_t *buf = nullptr;
+    IB200_TRY(cudaMalloc(&buf, (size_t)nnz * sizeof(int32_t) * 5));
+    int32_t *keys_a = buf, *keys_b = buf + nnz, *pos_a = buf + 2 * nnz, *pos_b = buf + 3 * nnz, *rowidx = buf + 4 * nnz;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    int64_t g = ceil_div(nnz, 256); if (g > cap) g = cap;
+    iota_rank_kernel<<<(unsigned)g, 256, 0, s>>>(nnz, colind, colrank, keys_a, pos_a);
+    count_launch();
+    expand_rows_kernel<<<(unsigned)ceil_div(m * 8, 256), 256, 0, s>>>(m, rowptr, rowidx);
+    count_launch();
+    count_keys_kernel<<<(unsigned)g, 256, 0, s>>>(nnz, keys_a, work);
     count_launch();
     int rc = exclusive_scan(s, k, work, t_rowptr, t_rowptr + k);
-    cudaFree(ctr);
-    if (rc) return rc;
-    int32_t *tmp_col = nullptr; c64 *tmp_val = nullptr;
-    IB200_TRY(cudaMalloc(&tmp_col, (size_t)nnz * sizeof(int32_t)));
-    cudaError_t e = cudaMalloc(&tmp_val, (size_t)nnz * sizeof(c64));
-    if (e != cudaSuccess) { cudaFree(tmp_col); IB200_TRY(e); }
-    cudaMemcpyAsync(work, t_rowptr, (size_t)k * sizeof(int32_t), cudaMemcpyDeviceToDevice, s);   // cursors
-    transpose_fill_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, s>>>(m, (const c64 *)vals, colind, rowptr, work,
-                                                                     tmp_col, tmp_val);
-    count_launch();
-    transpose_sort_kernel<<<(unsigned)ceil_div(k * 32, 256), 256, 0, s>>>(k, t_rowptr, tmp_col, tmp_val, t_colind,
-                                                                          (c64 *)t_vals);
-    count_launch();
-    e = cudaStreamSynchronize(s);
-    cudaFree(tmp_col); cudaFree(tmp_val);
+    if (rc) { cudaFree(buf); return rc; }
+    int end_bit = 1; while ((1LL << end_bit) < k) ++end_bit;
+    cub::DoubleBuffer<int32_t> dk(keys_a, keys_b), dv(pos_a, pos_b);
+    size_t tmp_bytes = 0;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int)nnz, 0, end_bit, s);
+    void *tmp = nullptr;
+    if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16);
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, (int)nnz, 0, end_bit, s);
+    if (e == cudaSuccess) {
+        count_launch(end_bit / 8 + 2);
+        transpose_gather_kernel<<<(unsigned)g, 256, 0, s>>>(nnz, dv.Current(), rowidx, (const c64 *)vals, t_colind,
+                                                            (c64 *)t_vals);
+        count_launch();
+        e = cudaStreamSynchronize(s);
+    }
+    cudaFree(tmp); cudaFree(buf);
     IB200_TRY(e);
     IB200_TRY(cudaGetLastError());
     return 0;

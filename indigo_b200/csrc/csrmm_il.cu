@@ -1,0 +1,320 @@
+// Coil-interleaved CSR SpMM: the multi-column fast path of Backend.ccsrmm.
+//
+// Interface served: Backend.ccsrmm (indigo/backends/backend.py:514-519) with
+// 2..32 right-hand-side columns (coils).  The interface hands X and Y over
+// column-major, coil = slowest axis (operators.py:27-31), so a CSR entry needs
+// one 8-byte gather per coil, `ld*8` bytes apart: at 125 entries per gridding
+// row and 16 coils every warp-wide load touches ~13 sectors in ~7 lines for 256
+// useful bytes and the kernel is bound by L1/L2 request throughput, not HBM
+// (measured: 873 GB/s algorithmic, 13 % of peak, profiles/r01_s1_*).
+//
+// Re-layout (north star: "multi-coil right-hand sides are read with vectorised,
+// coalesced loads"): X is transposed once into Xil[row][coil] (one pass at copy
+// bandwidth), after which the C coils of a grid point are ONE contiguous
+// C*8-byte segment -- a full 128-byte line for 16 coils.  A group of GL lanes
+// owns a matrix row: (index, value) pairs are fetched GL at a time with one
+// coalesced load and handed round by shuffles, lane (s, c) accumulates coil c
+// of every (GL/CL)-th entry, and the partial sums of the GL/CL slots are folded
+// with xor-shuffles.  The same kernel serves the forward gridding (rows =
+// samples, 125 entries) and the adjoint through the stored conjugate transpose
+// (rows = grid points, 0..2400 entries), so no atomics are needed anywhere.
+#include "common.cuh"
+
+namespace ib200 {
+
+// ---------------------------------------------------------------------------
+// X(rows x C, column-major, ld)  ->  Xil[r*pitch + c]
+static const int kTrRows = 64;
+
+template <bool POW2>
+__global__ void __launch_bounds__(256) interleave_kernel(int64_t rows, int C, int log2C, const c64 *__restrict__ X,
+                                                         int64_t ldx, c64 *__restrict__ Xil, int64_t pitch) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c64 *tile = reinterpret_cast<c64 *>(smem_raw);                 // [C][kTrRows + 1]
+    const int64_t r0 = (int64_t)blockIdx.x * kTrRows;
+    const int nr = rows - r0 < kTrRows ? (int)(rows - r0) : kTrRows;
+    const int r = threadIdx.x & (kTrRows - 1);
+    if (r < nr)
+        for (int c = threadIdx.x / kTrRows; c < C; c += 256 / kTrRows)
+            tile[c * (kTrRows + 1) + r] = __ldg(X + r0 + r + (int64_t)c * ldx);
+    __syncthreads();
+    const int n = nr * C;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const int rr = POW2 ? (i >> log2C) : (i / C);
+        const int c = POW2 ? (i & (C - 1)) : (i - rr * C);
+        Xil[(r0 + rr) * pitch + c] = tile[c * (kTrRows + 1) + rr];
+    }
+}
+
+// Y(rows x C, column-major, ld) = Yil^T + beta * Y      (beta == 0: Y is never read)
+template <bool POW2>
+__global__ void __launch_bounds__(256) deinterleave_kernel(int64_t rows, int C, int log2C,
+                                                           const c64 *__restrict__ Yil, int64_t pitch, c64 beta,
+                                                           int beta_zero, c64 *__restrict__ Y, int64_t ldy) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c64 *tile = reinterpret_cast<c64 *>(smem_raw);
+    const int64_t r0 = (int64_t)blockIdx.x * kTrRows;
+    const int nr = rows - r0 < kTrRows ? (int)(rows - r0) : kTrRows;
+    const int n = nr * C;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const int rr = POW2 ? (i >> log2C) : (i / C);
+        const int c = POW2 ? (i & (C - 1)) : (i - rr * C);
+        tile[c * (kTrRows + 1) + rr] = __ldg(Yil + (r0 + rr) * pitch + c);
+    }
+    __syncthreads();
+    const int r = threadIdx.x & (kTrRows - 1);
+    if (r < nr)
+        for (int c = threadIdx.x / kTrRows; c < C; c += 256 / kTrRows) {
+            c64 *yp = Y + r0 + r + (int64_t)c * ldy;
+            c64 v = tile[c * (kTrRows + 1) + r];
+            if (!beta_zero) v = cfma(beta, *yp, v);
+            *yp = v;
+        }
+}
+
+// ---------------------------------------------------------------------------
+// Yil[out(row)*ypitch + c] = alpha * sum_p vals[p] * Xil[colind[p]*xpitch + c]
+//
+// GL lanes per row, CL lanes per entry (one per coil), NP = GL/CL entries in flight per step.
+// A CTA owns GPB*rpg consecutive rows (GPB = 256/GL groups, rpg rows per group, interleaved so
+// that the groups always work on neighbouring rows): consecutive samples of a readout -- or the
+// grid points of one tile when the stored adjoint was built in tile-major order -- share most of
+// their operand lines, which then hit in L1.  Control flow is warp-uniform (trip counts are the
+// maximum over the groups of a warp, short rows are predicated off), so groups of one warp never
+// serialise.  Matrix entries are streamed with evict-first loads: they are used once, while the
+// operand rows are re-used from L2.  `rowmap` (optional) sends row r to output row rowmap[r]
+// (negative: padding row, nothing is written).
+template <int U>
+struct IlLoads {
+    c64 x[U];
+    float vx[U], vy[U];
+};
+
+template <int GL, int CL>
+__global__ void __launch_bounds__(256) csrmm_il_kernel(int64_t m, int C, c64 alpha, const c64 *__restrict__ vals,
+                                                       const int32_t *__restrict__ colind,
+                                                       const int32_t *__restrict__ rowptr,
+                                                       const c64 *__restrict__ Xil, uint32_t xpitch_bytes,
+                                                       c64 *__restrict__ Yil, int64_t ypitch,
+                                                       const int32_t *__restrict__ rowmap, int rpg) {
+    constexpr int NP = GL / CL, GPB = 256 / GL;
+    constexpr int U = CL >= 4 ? 4 : CL;                             // loads issued back to back
+    constexpr unsigned FULL = 0xffffffffu;
+    const int gl = (int)(threadIdx.x & (GL - 1));                   // lane within the group
+    const int coil = gl & (CL - 1);
+    const int slot = gl / CL;
+    const int group = (int)(threadIdx.x / GL);
+    const char *xb = reinterpret_cast<const char *>(Xil + (coil < C ? coil : 0));
+    const int64_t row0 = (int64_t)blockIdx.x * ((int64_t)GPB * rpg) + group;
+    for (int i = 0; i < rpg; ++i) {
+        const int64_t row = row0 + (int64_t)i * GPB;
+        int p0 = 0, len = 0;
+        if (row < m) { p0 = __ldg(rowptr + row); len = __ldg(rowptr + row + 1) - p0; }
+        int maxlen = len;
+#pragma unroll
+        for (int o = GL; o < 32; o <<= 1) { const int t = __shfl_xor_sync(FULL, maxlen, o); maxlen = t > maxlen ? t : maxlen; }
+        c64 acc = mk(0.f, 0.f);
+        for (int base = 0; base < maxlen; base += GL) {
+            const int left = len - base;                            // <= 0 once this group's row is done
+            int myc = 0;
+            c64 myv = mk(0.f, 0.f);
+            if (gl < left) { myc = __ldcs(colind + p0 + base + gl); myv = __ldcs(vals + p0 + base + gl); }
+            int minleft = left, maxleft = left;
+#pragma unroll
+            for (int o = GL; o < 32; o <<= 1) {
+                const int a = __shfl_xor_sync(FULL, minleft, o), b = __shfl_xor_sync(FULL, maxleft, o);
+                minleft = a < minleft ? a : minleft; maxleft = b > maxleft ? b : maxleft;
+            }
+            if (minleft >= GL) {                                    // every group of the warp has a full batch
+#pragma unroll
+                for (int t0 = 0; t0 < CL; t0 += U) {
+                    IlLoads<U> q;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int src = (t0 + u) * NP + slot;
+                        const unsigned c = (unsigned)__shfl_sync(FULL, myc, src, GL);
+                        q.vx[u] = __shfl_sync(FULL, myv.x, src, GL);
+                        q.vy[u] = __shfl_sync(FULL, myv.y, src, GL);
+                        q.x[u] = __ldg(reinterpret_cast<const c64 *>(xb + (uint64_t)c * xpitch_bytes));
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) acc = cfma(mk(q.vx[u], q.vy[u]), q.x[u], acc);
+                }
+            } else {
+                // ragged batch: lanes past the end of their row point at the row's first entry with
+                // weight 0, so every step is an unpredicated load of an address this row reads anyway
+                { const int c0 = __shfl_sync(FULL, myc, 0, GL); if (gl >= left) myc = c0; }
+                const int nsteps = maxleft >= GL ? CL : (maxleft + NP - 1) / NP;      // warp-uniform, <= CL
+                for (int t0 = 0; t0 < nsteps; t0 += U) {
+                    IlLoads<U> q;
+                    unsigned cc[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int src = (t0 + u) * NP + slot;       // < GL because CL is a multiple of U
+                        cc[u] = (unsigned)__shfl_sync(FULL, myc, src, GL);
+                        q.vx[u] = __shfl_sync(FULL, myv.x, src, GL);
+                        q.vy[u] = __shfl_sync(FULL, myv.y, src, GL);
+                    }
+                    if (left > 0) {                                 // uniform per group
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+                            q.x[u] = __ldg(reinterpret_cast<const c64 *>(xb + (uint64_t)cc[u] * xpitch_bytes));
+#pragma unroll
+                        for (int u = 0; u < U; ++u) acc = cfma(mk(q.vx[u], q.vy[u]), q.x[u], acc);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = CL; o < GL; o <<= 1) {
+            acc.x += __shfl_xor_sync(FULL, acc.x, o, GL);
+            acc.y += __shfl_xor_sync(FULL, acc.y, o, GL);
+        }
+        if (row < m && slot == 0 && coil < C) {
+            const int64_t out = rowmap ? (int64_t)__ldg(rowmap + row) : row;
+            if (out >= 0) __stcs(Yil + out * ypitch + coil, cmul(alpha, acc));
+        }
+    }
+}
+
+template <int GL, int CL>
+static int launch_il(cudaStream_t s, int64_t m, int C, c64 alpha, const c64 *vals, const int32_t *colind,
+                     const int32_t *rowptr, const c64 *Xil, int64_t xpitch, c64 *Yil, int64_t ypitch,
+                     const int32_t *rowmap, int rpg) {
+    const int64_t rows_per_cta = (int64_t)(256 / GL) * rpg;
+    const int64_t blocks = ceil_div(m, rows_per_cta);
+    IB200_REQUIRE(blocks < (1LL << 31), "matrix too large for one launch");
+    IB200_REQUIRE(xpitch * (int64_t)sizeof(c64) < (1LL << 32), "operand pitch too large");
+    csrmm_il_kernel<GL, CL><<<(unsigned)blocks, 256, 0, s>>>(m, C, alpha, vals, colind, rowptr, Xil,
+                                                             (uint32_t)(xpitch * sizeof(c64)), Yil, ypitch, rowmap, rpg);
+    IB200_LAUNCH_CHECK();
+    return 0;
+}
+
+// padded tile-major rank of every point of a 3-D grid (x fastest) and its inverse
+__global__ void __launch_bounds__(256) tile_rank_kernel(int n0, int n1, int n2, int t0, int t1, int t2,
+                                                        int32_t *__restrict__ colrank, int32_t *__restrict__ rowmap) {
+    const int nt0 = (n0 + t0 - 1) / t0, nt1 = (n1 + t1 - 1) / t1, nt2 = (n2 + t2 - 1) / t2;
+    const int64_t padded = (int64_t)nt0 * nt1 * nt2 * t0 * t1 * t2;
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    const int tvol = t0 * t1 * t2;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < padded; r += nth) {
+        const int64_t tile = r / tvol;
+        const int w = (int)(r - tile * tvol);
+        const int wx = w % t0, wy = (w / t0) % t1, wz = w / (t0 * t1);
+        const int tx = (int)(tile % nt0), ty = (int)((tile / nt0) % nt1), tz = (int)(tile / ((int64_t)nt0 * nt1));
+        const int x = tx * t0 + wx, y = ty * t1 + wy, z = tz * t2 + wz;
+        if (x < n0 && y < n1 && z < n2) {
+            const int64_t g = ((int64_t)z * n1 + y) * n0 + x;
+            rowmap[r] = (int32_t)g;
+            colrank[g] = (int32_t)r;
+        } else {
+            rowmap[r] = -1;
+        }
+    }
+}
+
+static int pow2_ceil(int64_t v) { int p = 1; while (p < v) p <<= 1; return p; }
+static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+}  // namespace ib200
+
+using namespace ib200;
+
+extern "C" {
+
+int ib200_interleave(void *stream, int64_t rows, int64_t ncols, const void *X, int64_t ldx, void *Xil, int64_t pitch) {
+    IB200_REQUIRE(rows >= 0 && ncols >= 0, "negative dimension");
+    if (rows == 0 || ncols == 0) return 0;
+    IB200_REQUIRE(X && Xil, "null pointer");
+    IB200_REQUIRE(ncols <= 1024 && pitch >= ncols && (ncols == 1 || ldx >= rows), "bad column count / pitch / ld");
+    const int C = (int)ncols;
+    const size_t smem = (size_t)C * (kTrRows + 1) * sizeof(c64);
+    IB200_REQUIRE((int64_t)smem <= 48 * 1024, "too many columns for the transposing tile (max 94)");
+    const int64_t blocks = ceil_div(rows, kTrRows);
+    IB200_REQUIRE(blocks < (1LL << 31), "too many rows for one launch");
+    const bool p2 = (C & (C - 1)) == 0;
+    if (p2) interleave_kernel<true><<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(rows, C, ilog2(C), (const c64 *)X, ldx, (c64 *)Xil, pitch);
+    else    interleave_kernel<false><<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(rows, C, 0, (const c64 *)X, ldx, (c64 *)Xil, pitch);
+    IB200_LAUNCH_CHECK();
+    return 0;
+}
+
+int ib200_deinterleave(void *stream, int64_t rows, int64_t ncols, const void *Yil, int64_t pitch, float br, float bi,
+                       void *Y, int64_t ldy) {
+    IB200_REQUIRE(rows >= 0 && ncols >= 0, "negative dimension");
+    if (rows == 0 || ncols == 0) return 0;
+    IB200_REQUIRE(Y && Yil, "null pointer");
+    IB200_REQUIRE(ncols <= 1024 && pitch >= ncols && (ncols == 1 || ldy >= rows), "bad column count / pitch / ld");
+    const int C = (int)ncols;
+    const size_t smem = (size_t)C * (kTrRows + 1) * sizeof(c64);
+    IB200_REQUIRE((int64_t)smem <= 48 * 1024, "too many columns for the transposing tile (max 94)");
+    const int64_t blocks = ceil_div(rows, kTrRows);
+    IB200_REQUIRE(blocks < (1LL << 31), "too many rows for one launch");
+    const int b0 = (br == 0.f && bi == 0.f) ? 1 : 0;
+    const bool p2 = (C & (C - 1)) == 0;
+    if (p2) deinterleave_kernel<true><<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(rows, C, ilog2(C), (const c64 *)Yil, pitch, mk(br, bi), b0, (c64 *)Y, ldy);
+    else    deinterleave_kernel<false><<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(rows, C, 0, (const c64 *)Yil, pitch, mk(br, bi), b0, (c64 *)Y, ldy);
+    IB200_LAUNCH_CHECK();
+    return 0;
+}
+
+int ib200_ccsrmm_il(void *stream, int64_t m, int64_t k, int64_t ncols, int64_t nnz, float ar, float ai,
+                    const void *vals, const int32_t *colind, const int32_t *rowptr, const void *Xil, int64_t xpitch,
+                    void *Yil, int64_t ypitch, const int32_t *rowmap, int rows_per_group) {
+    IB200_REQUIRE(m >= 0 && k >= 0 && ncols >= 0 && nnz >= 0, "negative dimension");
+    IB200_REQUIRE(m < (1LL << 31) && k < (1LL << 31) && nnz < (1LL << 31), "int32 CSR indices: dimensions must be < 2^31");
+    IB200_REQUIRE(ncols <= 32, "interleaved SpMM serves at most 32 columns per call");
+    if (m == 0 || ncols == 0) return 0;
+    IB200_REQUIRE(rowptr && Yil && (nnz == 0 || (vals && colind && Xil)), "null pointer");
+    IB200_REQUIRE(xpitch >= ncols && ypitch >= ncols, "pitch smaller than the column count");
+    IB200_REQUIRE(rows_per_group >= 0 && rows_per_group <= 4096, "rows_per_group out of range");
+    const int CL = pow2_ceil(ncols);
+    // lanes per row: at least one per coil, more when rows are long enough to feed them
+    const double avg = (double)nnz / (double)m;
+    int GL = CL;
+    while (GL < 32 && avg >= 1.5 * GL) GL <<= 1;
+    if (CL == 16 && GL == 32 && avg < 64) GL = 16;
+    // rows per group: 0 = automatic (long rows: 32 consecutive rows per CTA; short rows: one pass)
+    int rpg = rows_per_group;
+    if (rpg == 0) rpg = avg >= 32 ? (32 * GL) / 256 : 1;
+    if (rpg < 1) rpg = 1;
+    const c64 alpha = mk(ar, ai);
+    cudaStream_t s = as_stream(stream);
+#define IB200_IL_CASE(gl, cl) \
+    case (gl) * 100 + (cl): return launch_il<gl, cl>(s, m, (int)ncols, alpha, (const c64 *)vals, colind, rowptr, (const c64 *)Xil, xpitch, (c64 *)Yil, ypitch, rowmap, rpg)
+    switch (GL * 100 + CL) {
+        IB200_IL_CASE(1, 1);
+        IB200_IL_CASE(2, 1); IB200_IL_CASE(2, 2);
+        IB200_IL_CASE(4, 1); IB200_IL_CASE(4, 2); IB200_IL_CASE(4, 4);
+        IB200_IL_CASE(8, 1); IB200_IL_CASE(8, 2); IB200_IL_CASE(8, 4); IB200_IL_CASE(8, 8);
+        IB200_IL_CASE(16, 1); IB200_IL_CASE(16, 2); IB200_IL_CASE(16, 4); IB200_IL_CASE(16, 8); IB200_IL_CASE(16, 16);
+        IB200_IL_CASE(32, 1); IB200_IL_CASE(32, 2); IB200_IL_CASE(32, 4); IB200_IL_CASE(32, 8); IB200_IL_CASE(32, 16);
+        IB200_IL_CASE(32, 32);
+    }
+#undef IB200_IL_CASE
+    set_error("internal: no interleaved kernel for GL=%d CL=%d", GL, CL);
+    return IB200_E_UNSUPPORTED;
+}
+
+int ib200_grid_tile_rank(void *stream, const int64_t grid[3], const int64_t tile[3], int32_t *colrank, int32_t *rowmap,
+                         int64_t *padded_rows) {
+    IB200_REQUIRE(grid && tile && padded_rows, "null pointer");
+    int64_t padded = 1, plain = 1;
+    for (int d = 0; d < 3; ++d) {
+        IB200_REQUIRE(grid[d] > 0 && tile[d] > 0 && tile[d] <= 64, "bad grid / tile extent");
+        padded *= ceil_div(grid[d], tile[d]) * tile[d];
+        plain *= grid[d];
+    }
+    IB200_REQUIRE(padded < (1LL << 31), "padded grid must hold fewer than 2^31 points");
+    *padded_rows = padded;
+    if (!colrank && !rowmap) return 0;                           // size query
+    IB200_REQUIRE(colrank && rowmap, "null pointer");
+    int64_t g = ceil_div(padded, 256); const int64_t cap = (int64_t)sm_count() * 16; if (g > cap) g = cap;
+    tile_rank_kernel<<<(unsigned)g, 256, 0, as_stream(stream)>>>((int)grid[0], (int)grid[1], (int)grid[2], (int)tile[0],
+                                                                (int)tile[1], (int)tile[2], colrank, rowmap);
+    IB200_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

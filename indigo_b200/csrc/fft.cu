@@ -17,6 +17,7 @@
 // Tile logic lives in fft_core.cuh, planning in fft_plan.hpp (both shared with
 // the CPU emulation harness used by the GPU-less tests).
 #include "fft_plan.hpp"
+#include "fft_il.cuh"
 
 #include <cstdlib>
 #include <new>
@@ -76,6 +77,53 @@ static int try_spec(cudaStream_t s, bool axis0, const FftKernelArgs &k) {
     IB200_FFT_SPEC_LIST(IB200_TRY_SPEC)
 #undef IB200_TRY_SPEC
     return 0;
+}
+
+// ---- fused SENSE x passes on the interleaved grid (fft_il.cuh) ---------------------------------
+template <int N, int R0, int R1, int R2>
+__global__ void __launch_bounds__(256, 2) sense_expand_kernel(const SenseFftArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    sense_expand_body<N, R0, R1, R2>(a, reinterpret_cast<c64 *>(smem_raw), (int64_t)blockIdx.x, (int)threadIdx.x,
+                                     (int)blockDim.x);
+}
+
+template <int N, int R0, int R1, int R2>
+__global__ void __launch_bounds__(256, 2) sense_combine_kernel(const SenseFftArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c64 *buf = reinterpret_cast<c64 *>(smem_raw);
+    sense_combine_body<N, R0, R1, R2>(a, buf, buf + (size_t)2 * N * kSpecLP, (int64_t)blockIdx.x, (int)threadIdx.x,
+                                      (int)blockDim.x);
+}
+
+template <int N, int R0, int R1, int R2>
+static int launch_sense_x(cudaStream_t s, bool combine, const SenseFftArgs &a) {
+    static bool attr_done[2][64] = {{false}};
+    const size_t smem = (size_t)2 * N * kSpecLP * sizeof(c64) + (combine ? (size_t)a.N0 * sizeof(c64) : 0);
+    IB200_REQUIRE((int64_t)smem <= smem_optin(), "sense x pass: tile does not fit shared memory");
+    int dev = 0;
+    IB200_TRY(cudaGetDevice(&dev));
+    if (!attr_done[combine ? 1 : 0][dev & 63]) {
+        if (combine) IB200_TRY(cudaFuncSetAttribute(sense_combine_kernel<N, R0, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin()));
+        else         IB200_TRY(cudaFuncSetAttribute(sense_expand_kernel<N, R0, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin()));
+        attr_done[combine ? 1 : 0][dev & 63] = true;
+    }
+    const int64_t blocks = (int64_t)a.N1 * a.N2;
+    IB200_REQUIRE(blocks < (1LL << 31), "sense x pass: too many rows for one launch");
+    if (combine) sense_combine_kernel<N, R0, R1, R2><<<(unsigned)blocks, 256, smem, s>>>(a);
+    else         sense_expand_kernel<N, R0, R1, R2><<<(unsigned)blocks, 256, smem, s>>>(a);
+    IB200_LAUNCH_CHECK();
+    return 0;
+}
+
+static int run_sense_x(cudaStream_t s, bool combine, const SenseFftArgs &a, const FftStages &st) {
+    FftKernelArgs k;
+    k.n = a.n0; k.st = st;
+#define IB200_SENSE_X(n, r0, r1, r2) \
+    if (fft_spec_matches(k, n, r0, r1, r2)) return launch_sense_x<n, r0, r1, r2>(s, combine, a);
+    IB200_FFT_SPEC_LIST(IB200_SENSE_X)
+#undef IB200_SENSE_X
+    set_error("fused SENSE passes need a grid extent with a specialised FFT (got %d)", a.n0);
+    return IB200_E_UNSUPPORTED;
 }
 
 }  // namespace ib200
@@ -176,6 +224,121 @@ int ib200_fft_exec_diag(ib200_fft_plan plan, void *stream, void *y, const void *
     IB200_REQUIRE(plan, "null plan");
     return exec_impl(&plan->d, as_stream(stream), (c64 *)y, (const c64 *)x, direction, (const c64 *)d_in, conj_in,
                      (const c64 *)d_out, conj_out);
+}
+
+/* ---- fused SENSE transforms (see include/indigo_b200.h) ---------------------------------------- */
+struct ib200_sense_plan_s {
+    ib200_fft_plan fft;
+    int64_t N[3], oN[3], off[3];
+    int64_t C;
+};
+
+static int sense_strided_pass(ib200_sense_plan_s *p, cudaStream_t s, c64 *grid, int axis, bool inverse, bool first,
+                              bool last) {
+    // axis 1: lines are the (x, c) pairs of one y row, one slab per z of the image window;
+    // axis 2: lines are all (y, x, c) triples, a single slab.
+    const FftPlanData &pl = p->fft->d;
+    const AxisPlan &ax = pl.ax[axis];
+    const int64_t sy = p->oN[0] * p->C, sz = sy * p->oN[1];
+    FftKernelArgs k;
+    k.tw = ax.tw_dev; k.din = k.dout = nullptr; k.conj_in = k.conj_out = 0;
+    k.plane = 0;
+    k.n = ax.n; k.L = kSpecL; k.log2L = 4;
+    k.swap_in = (inverse && first) ? 1 : 0; k.swap_out = (inverse && last) ? 1 : 0;
+    k.load_first = 0; k.store_last = 0;
+    k.st = ax.st;
+    const int w0 = (int)p->off[axis], w1 = (int)(p->off[axis] + p->N[axis]);
+    if (!inverse) { k.in0 = w0; k.in1 = w1; k.out0 = 0; k.out1 = ax.n; }
+    else          { k.in0 = 0; k.in1 = ax.n; k.out0 = w0; k.out1 = w1; }
+    c64 *base = grid;
+    if (axis == 1) {
+        k.inner = sy; k.outer = p->N[2]; k.outer_stride = sz;
+        base = grid + p->off[2] * sz;
+    } else {
+        k.inner = sz; k.outer = 1; k.outer_stride = sz * p->oN[2];
+    }
+    k.x = base; k.y = base;
+    const int rc = try_spec(s, false, k);
+    if (rc == 1) return 0;
+    if (rc == 0) { set_error("fused SENSE passes need a grid extent with a specialised FFT (axis %d: %d)", axis, ax.n); return IB200_E_UNSUPPORTED; }
+    return rc > 1000 ? rc - 1000 : rc;
+}
+
+int ib200_sense_plan_create(ib200_sense_plan *plan, const int64_t N[3], const int64_t oN[3], int64_t ncoils) {
+    IB200_REQUIRE(plan && N && oN, "null pointer");
+    IB200_REQUIRE(ncoils >= 1, "need at least one coil");
+    for (int d = 0; d < 3; ++d) IB200_REQUIRE(N[d] >= 1 && oN[d] >= N[d], "grid must be at least as large as the image");
+    ib200_sense_plan_s *p = new (std::nothrow) ib200_sense_plan_s();
+    if (!p) { set_error("out of host memory"); return IB200_E_NOMEM; }
+    int rc = ib200_fft_plan_create(&p->fft, 3, oN, ncoils);
+    if (rc) { delete p; return rc; }
+    for (int d = 0; d < 3; ++d) {
+        p->N[d] = N[d]; p->oN[d] = oN[d];
+        p->off[d] = oN[d] / 2 - N[d] / 2;                       // Zpad 'center': oN//2 + ceil(-N/2), backend.py:379-381
+        FftKernelArgs k; k.n = (int)oN[d]; k.st = p->fft->d.ax[d].st;
+        bool ok = false;
+#define IB200_SENSE_OK(n, r0, r1, r2) ok = ok || fft_spec_matches(k, n, r0, r1, r2);
+        IB200_FFT_SPEC_LIST(IB200_SENSE_OK)
+#undef IB200_SENSE_OK
+        if (!ok) {
+            set_error("fused SENSE passes: grid extent %lld has no specialised FFT", (long long)oN[d]);
+            ib200_fft_plan_destroy(p->fft); delete p;
+            return IB200_E_UNSUPPORTED;
+        }
+    }
+    IB200_REQUIRE(oN[0] * ncoils >= kSpecL, "grid row too short");
+    p->C = ncoils;
+    *plan = p;
+    return 0;
+}
+
+int ib200_sense_plan_destroy(ib200_sense_plan plan) {
+    if (!plan) return 0;
+    ib200_fft_plan_destroy(plan->fft);
+    delete plan;
+    return 0;
+}
+
+static void sense_args(ib200_sense_plan_s *p, SenseFftArgs *a) {
+    a->N0 = (int)p->N[0]; a->N1 = (int)p->N[1]; a->N2 = (int)p->N[2];
+    a->n0 = (int)p->oN[0]; a->n1 = (int)p->oN[1]; a->n2 = (int)p->oN[2];
+    a->off0 = (int)p->off[0]; a->off1 = (int)p->off[1]; a->off2 = (int)p->off[2];
+    a->C = (int)p->C;
+    a->tw = p->fft->d.ax[0].tw_dev;
+    a->img = nullptr; a->img_out = nullptr; a->pf = nullptr; a->grid = nullptr;
+    a->alpha = mk(1.f, 0.f); a->beta = mk(0.f, 0.f); a->beta_zero = 1;
+}
+
+int ib200_sense_expand_fft(ib200_sense_plan plan, void *stream, void *grid_il, const void *img, const void *pf) {
+    IB200_REQUIRE(plan && grid_il && img && pf, "null pointer");
+    int rc = ensure_device_state(&plan->fft->d);
+    if (rc) return rc;
+    cudaStream_t s = as_stream(stream);
+    SenseFftArgs a;
+    sense_args(plan, &a);
+    a.img = (const c64 *)img; a.pf = (const c64 *)pf; a.grid = (c64 *)grid_il;
+    rc = run_sense_x(s, false, a, plan->fft->d.ax[0].st);
+    if (rc) return rc;
+    rc = sense_strided_pass(plan, s, (c64 *)grid_il, 1, false, false, false);
+    if (rc) return rc;
+    return sense_strided_pass(plan, s, (c64 *)grid_il, 2, false, false, true);
+}
+
+int ib200_sense_ifft_combine(ib200_sense_plan plan, void *stream, void *img_out, void *grid_il, const void *pf,
+                             float ar, float ai, float br, float bi) {
+    IB200_REQUIRE(plan && grid_il && img_out && pf, "null pointer");
+    int rc = ensure_device_state(&plan->fft->d);
+    if (rc) return rc;
+    cudaStream_t s = as_stream(stream);
+    rc = sense_strided_pass(plan, s, (c64 *)grid_il, 2, true, true, false);
+    if (rc) return rc;
+    rc = sense_strided_pass(plan, s, (c64 *)grid_il, 1, true, false, false);
+    if (rc) return rc;
+    SenseFftArgs a;
+    sense_args(plan, &a);
+    a.img_out = (c64 *)img_out; a.pf = (const c64 *)pf; a.grid = (c64 *)grid_il;
+    a.alpha = mk(ar, ai); a.beta = mk(br, bi); a.beta_zero = (br == 0.f && bi == 0.f) ? 1 : 0;
+    return run_sense_x(s, true, a, plan->fft->d.ax[0].st);
 }
 
 }  // extern "C"

@@ -152,9 +152,12 @@ struct FftCtx {
     const c64 *dout;       // optional diagonal on store
     int n, L, log2L, LP, nl;
     int swap_in, swap_out, conj_in, conj_out;
+    int in0, in1;          // positions outside [in0, in1) read as zero without touching memory (pruned input)
+    int out0, out1;        // positions outside [out0, out1) are not stored (pruned output)
 };
 
 IB_HD c64 fft_gload(const FftCtx &c, int l, int j) {
+    if (j < c.in0 || j >= c.in1) return h_mk(0.f, 0.f);
     const int64_t off = (int64_t)l * c.gstride_l + (int64_t)j * c.gstride_j;
     c64 v = c.gin[off];
     if (c.din) { const c64 d = c.din[off]; v = c.conj_in ? h_mulc(v, d) : h_mul(v, d); }
@@ -162,6 +165,7 @@ IB_HD c64 fft_gload(const FftCtx &c, int l, int j) {
 }
 
 IB_HD void fft_gstore(const FftCtx &c, int l, int j, c64 v) {
+    if (j < c.out0 || j >= c.out1) return;
     const int64_t off = (int64_t)l * c.gstride_l + (int64_t)j * c.gstride_j;
     if (c.swap_out) v = h_swap(v);
     if (c.dout) { const c64 d = c.dout[off]; v = c.conj_out ? h_mulc(v, d) : h_mul(v, d); }
@@ -263,6 +267,8 @@ struct FftKernelArgs {
     int n, L, log2L;
     int swap_in, swap_out, conj_in, conj_out;
     int load_first, store_last;
+    int in0, in1, out0, out1;       // input / output windows along the transformed axis (see FftCtx)
+    int64_t outer_stride;           // elements between consecutive outer slabs (n*inner when dense)
     FftStages st;
 };
 
@@ -308,6 +314,7 @@ IB_HD void fft_pass_body(const FftKernelArgs &a, c64 *bufA, int64_t block, int t
     c.n = a.n; c.L = a.L; c.log2L = a.log2L; c.LP = a.L + 1;
     c.tw = a.tw;
     c.swap_in = a.swap_in; c.swap_out = a.swap_out; c.conj_in = a.conj_in; c.conj_out = a.conj_out;
+    c.in0 = a.in0; c.in1 = a.in1; c.out0 = a.out0; c.out1 = a.out1;
     c64 *bufB = bufA + (size_t)a.n * c.LP;
 
     int64_t base;
@@ -323,7 +330,7 @@ IB_HD void fft_pass_body(const FftKernelArgs &a, c64 *bufA, int64_t block, int t
         const int64_t s0 = ts * a.L;
         const int64_t left = a.inner - s0;
         c.nl = left < a.L ? (int)left : a.L;
-        base = o * a.n * a.inner + s0;
+        base = o * a.outer_stride + s0;
         c.gstride_j = a.inner; c.gstride_l = 1;
     }
     c.gin = a.x + base; c.gout = a.y + base;
@@ -461,6 +468,7 @@ IB_HD void fft_pass_body_spec(const FftKernelArgs &a, c64 *bufA, int64_t block, 
     c.n = N; c.L = kSpecL; c.log2L = 4; c.LP = kSpecLP;
     c.tw = a.tw;
     c.swap_in = a.swap_in; c.swap_out = a.swap_out; c.conj_in = a.conj_in; c.conj_out = a.conj_out;
+    c.in0 = a.in0; c.in1 = a.in1; c.out0 = a.out0; c.out1 = a.out1;
     c64 *bufB = bufA + (size_t)N * kSpecLP;
     int64_t base;
     if (AXIS0) {
@@ -472,7 +480,7 @@ IB_HD void fft_pass_body_spec(const FftKernelArgs &a, c64 *bufA, int64_t block, 
         const int64_t tiles = (a.inner + kSpecL - 1) / kSpecL;
         const int64_t o = block / tiles, s0 = (block % tiles) * kSpecL, left = a.inner - s0;
         c.nl = left < kSpecL ? (int)left : kSpecL;
-        base = o * N * a.inner + s0;
+        base = o * a.outer_stride + s0;
         c.gstride_j = a.inner; c.gstride_l = 1;
     }
     c.gin = a.x + base; c.gout = a.y + base;

@@ -1,0 +1,131 @@
+// Fused SENSE passes on the coil-interleaved oversampled grid
+//     grid[z][y][x][c]      (c fastest; x, y, z over the oversampled extents n0, n1, n2)
+// shared by the device kernels (fft.cu) and the CPU emulation (tests/csrc/fft_emul.cu).
+//
+// Reference calls being fused:
+//   ccsrmm(P^H, adjoint)  +  fftn          ->  sense_expand_body  + two windowed strided passes
+//   ifftn  +  ccsrmm(P^H)                  ->  two windowed strided passes + sense_combine_body
+// with P = kron(I_C, mod*zpad*apod) * vstack(maps) (examples/pics.py:111-126): the coil maps,
+// apodisation and centring phase are one dense factor pf[voxel][coil], zero-padding is the input
+// window of each pass (rows outside the image are never read, written or transformed before the
+// pass that creates them) and the crop is the output window.
+//
+// In this layout every axis is a "strided" axis whose 16 neighbouring lines are the 16 coils
+// (or 16 consecutive (x, c) pairs) of one 128-byte segment, so all three passes use the
+// lines-fast Stockham stages of fft_core.cuh.
+#pragma once
+#include "fft_core.cuh"
+
+namespace ib200 {
+
+struct SenseFftArgs {
+    const c64 *img;        // expand: image, N0*N1*N2, x fastest
+    c64 *img_out;          // combine: image to update
+    const c64 *pf;         // [voxel][coil] = q[voxel] * maps[voxel, coil]
+    c64 *grid;             // interleaved oversampled grid, n0*n1*n2*C
+    const c64 *tw;         // n0 twiddles
+    int N0, N1, N2;
+    int n0, n1, n2;
+    int off0, off1, off2;  // position of the image inside the grid (Zpad 'center', backend.py:371-387)
+    int C;
+    c64 alpha, beta;
+    int beta_zero;
+};
+
+// x pass of the forward transform: grid[z+off2][y+off1][:][c] = FFT_x( zpad( img[:, y, z] * pf[., c] ) )
+// one CTA per image row (y, z); coils in chunks of 16 lines.
+template <int N, int R0, int R1, int R2>
+IB_HD void sense_expand_body(const SenseFftArgs &a, c64 *bufA, int64_t block, int tid, int nt) {
+    constexpr bool THREE = R2 > 1;
+    c64 *bufB = bufA + (size_t)N * kSpecLP;
+    const int y = (int)(block % a.N1), z = (int)(block / a.N1);
+    const int64_t vox0 = ((int64_t)z * a.N1 + y) * a.N0;
+    FftCtx c;
+    c.n = N; c.L = kSpecL; c.log2L = 4; c.LP = kSpecLP; c.tw = a.tw;
+    c.swap_in = c.swap_out = c.conj_in = c.conj_out = 0;
+    c.din = c.dout = nullptr;
+    c.in0 = 0; c.in1 = N; c.out0 = 0; c.out1 = N;
+    c.gstride_j = a.C; c.gstride_l = 1;
+    c.gin = nullptr;
+    const int64_t row = ((int64_t)(z + a.off2) * a.n1 + (y + a.off1)) * (int64_t)a.n0 * a.C;
+    for (int c0 = 0; c0 < a.C; c0 += kSpecL) {
+        c.nl = a.C - c0 < kSpecL ? a.C - c0 : kSpecL;
+        c.gout = a.grid + row + c0;
+        for (int idx = tid; idx < N * kSpecL; idx += nt) {
+            const int l = idx & (kSpecL - 1), pos = idx >> 4;
+            if (l >= c.nl) continue;
+            const int j = pos - a.off0;
+            c64 v = h_mk(0.f, 0.f);
+            if (j >= 0 && j < a.N0) v = h_mul(a.img[vox0 + j], a.pf[(vox0 + j) * a.C + c0 + l]);
+            bufA[spec_addr<0>(pos, l)] = v;
+        }
+        IB_SYNC();
+        spec_stage_lfast<N, R0, 1, false, false, 0, 0>(c, bufA, bufB, tid, nt);
+        IB_SYNC();
+        if (THREE) {
+            spec_stage_lfast<N, R1, R0, false, false, 0, 0>(c, bufB, bufA, tid, nt);
+            IB_SYNC();
+            spec_stage_lfast<N, THREE ? R2 : R1, R0 * R1, false, true, 0, 0>(c, bufA, nullptr, tid, nt);
+        } else {
+            spec_stage_lfast<N, R1, R0, false, true, 0, 0>(c, bufB, nullptr, tid, nt);
+        }
+        IB_SYNC();
+    }
+}
+
+// x pass of the inverse transform with the coil combination:
+//   img_out[:, y, z] = alpha * sum_c conj(pf[., c]) * crop( IFFT_x( grid[z+off2][y+off1][:][c] ) ) + beta * img_out
+// The re/im swap that turns the forward butterflies into the inverse transform was applied on the
+// load of the first inverse pass (z); this is the last pass, so it swaps back before the product.
+// `acc` is N0 complex words of shared memory.
+template <int N, int R0, int R1, int R2>
+IB_HD void sense_combine_body(const SenseFftArgs &a, c64 *bufA, c64 *acc, int64_t block, int tid, int nt) {
+    constexpr bool THREE = R2 > 1;
+    c64 *bufB = bufA + (size_t)N * kSpecLP;
+    const int y = (int)(block % a.N1), z = (int)(block / a.N1);
+    const int64_t vox0 = ((int64_t)z * a.N1 + y) * a.N0;
+    FftCtx c;
+    c.n = N; c.L = kSpecL; c.log2L = 4; c.LP = kSpecLP; c.tw = a.tw;
+    c.swap_in = c.swap_out = c.conj_in = c.conj_out = 0;
+    c.din = c.dout = nullptr;
+    c.in0 = 0; c.in1 = N; c.out0 = 0; c.out1 = N;
+    c.gstride_j = a.C; c.gstride_l = 1;
+    c.gout = nullptr;
+    const int64_t row = ((int64_t)(z + a.off2) * a.n1 + (y + a.off1)) * (int64_t)a.n0 * a.C;
+    for (int c0 = 0; c0 < a.C; c0 += kSpecL) {
+        c.nl = a.C - c0 < kSpecL ? a.C - c0 : kSpecL;
+        c.gin = a.grid + row + c0;
+        spec_stage_lfast<N, R0, 1, true, false, 0, 0>(c, nullptr, bufA, tid, nt);
+        IB_SYNC();
+        spec_stage_lfast<N, R1, R0, false, false, 0, 0>(c, bufA, bufB, tid, nt);
+        IB_SYNC();
+        c64 *res = bufB;
+        if (THREE) {
+            spec_stage_lfast<N, THREE ? R2 : R1, R0 * R1, false, false, 0, 0>(c, bufB, bufA, tid, nt);
+            IB_SYNC();
+            res = bufA;
+        }
+        // multiply the cropped positions by conj(pf) in place (coil index fastest: coalesced pf reads) ...
+        for (int idx = tid; idx < a.N0 * kSpecL; idx += nt) {
+            const int l = idx & (kSpecL - 1), j = idx >> 4;
+            if (l >= c.nl) continue;
+            const int at = spec_addr<0>(j + a.off0, l);
+            res[at] = h_mulc(h_swap(res[at]), a.pf[(vox0 + j) * a.C + c0 + l]);
+        }
+        IB_SYNC();
+        // ... and fold the coils of each position
+        for (int j = tid; j < a.N0; j += nt) {
+            c64 s = c0 == 0 ? h_mk(0.f, 0.f) : acc[j];
+            for (int l = 0; l < c.nl; ++l) s = h_add(s, res[spec_addr<0>(j + a.off0, l)]);
+            acc[j] = s;
+        }
+        IB_SYNC();
+    }
+    for (int j = tid; j < a.N0; j += nt) {
+        c64 v = h_mul(a.alpha, acc[j]);
+        if (!a.beta_zero) v = h_add(v, h_mul(a.beta, a.img_out[vox0 + j]));
+        a.img_out[vox0 + j] = v;
+    }
+}
+
+}  // namespace ib200

@@ -153,6 +153,8 @@ int fft_exec_passes(const FftPlanData *pl, c64 *y, const c64 *x, int direction, 
         k.n = ax.n; k.L = g.L; k.log2L = fft_ilog2(g.L);
         k.swap_in = (inv && first) ? 1 : 0; k.swap_out = (inv && last) ? 1 : 0;
         k.load_first = g.load_first; k.store_last = g.store_last;
+        k.in0 = 0; k.in1 = ax.n; k.out0 = 0; k.out1 = ax.n;
+        k.outer_stride = (int64_t)ax.n * inner;
         k.st = ax.st;
         const int64_t blocks = axis0 ? ceil_div(outer, g.L) : ceil_div(inner, g.L) * outer;
         IB200_REQUIRE(blocks < (1LL << 31), "fft: too many tiles for one launch");

@@ -1,0 +1,184 @@
+"""
+Backend-specific fusion of the SENSE-NUFFT operator (the
+north star's "fused elementwise" item).
+
+The reference's -O3 tree evaluates A^H A as six Backend calls
+    ccsrmm(P^H, adj) -> fftn -> ccsrmm(G') -> ccsrmm(G', adj) -> ifftn -> ccsrmm(P^H)
+on column-major (grid, coil) arrays.  On the B200 the same
+arithmetic runs as
+
+    ib200_sense_expand_fft      grid = FFT3(zpad(pf .* x))           coil-interleaved grid[z][y][x][c],
+                                                                      zero rows never touched (pruned passes)
+    ib200_ccsrmm_il  (G')       k    = G' grid                        one 128-byte line per stored entry
+    ib200_ccsrmm_il  (G'^H)     grid = G'^H k                         stored adjoint, rows in tile-major order
+    ib200_sense_ifft_combine    y    = sum_c conj(pf) .* crop(IFFT3(grid))
+
+so the 9.2 GB zero-padded volume of cfg3 is never written by a scatter, read back by the FFT,
+or transposed between the coil-slow layout of the interface and the coil-fast layout the
+gather wants.  The node below is an ordinary operator of the tree family the backend uses
+(`B.ops.Operator`): `A * x`, `A.H * y`, `(A.H * A) * x`, `B.cg(A.H * A, ...)` work as for the
+unfused tree, and tests/test_gpu_fused.py checks all of them against the same oracle.
+"""
+import ctypes
+
+import numpy as np
+
+_C64 = np.dtype('complex64')
+
+
+class SenseDevice(object):
+    """Device-resident pieces shared by the fused nodes of one SENSE operator."""
+
+    tile = (4, 4, 4)
+
+    def __init__(self, B, N, coord, maps, oversamp=2.0, weights=None, width=3, n=128):
+        from .sense import gridding_matrix_device, _fftc_mod
+        from .host.noncart import rolloff3
+
+        self.B = B
+        lib, s = B._lib, B._stream
+        N = tuple(int(v) for v in N)
+        C = int(maps.shape[3])
+        self.G, oN, omin, beta = gridding_matrix_device(B, N, coord, oversamp, weights, width, n)
+        self.N, self.oN, self.C = N, tuple(int(v) for v in oN), C
+        self.M = int(self.G.shape[0])
+        self.nvox, self.on = int(np.prod(N)), int(np.prod(oN))
+        self.nnz = int(self.G.values.size)
+        # fused plan first: raises RuntimeError (unsupported) for grids without specialised passes
+        n3, on3 = (ctypes.c_int64 * 3)(*N), (ctypes.c_int64 * 3)(*self.oN)
+        self._plan = ctypes.c_void_p()
+        lib.sense_plan_create(ctypes.byref(self._plan), n3, on3, C)
+        # pf[voxel][coil] = (mod[zp] * apod)[voxel] * maps[voxel, coil]  (the factor P of pics.py:111-126)
+        cut = tuple(slice(a // 2 + int(np.ceil(-b / 2)), a // 2 + int(np.ceil(b / 2))) for a, b in zip(self.oN, N))
+        mod_at = _fftc_mod(self.oN)[cut].flatten(order='F')
+        apod = rolloff3(omin, width, beta, N).flatten(order='F').astype(_C64)
+        q = (mod_at * np.complex64(1)) * apod
+        maps_f = maps.reshape((self.nvox, C), order='F').astype(_C64)
+        self.pf = B.copy_array(np.ascontiguousarray(q[:, None] * maps_f).reshape(-1))
+        # stored adjoint of G' with the grid points in (padded) tile-major order
+        grid3, tile3 = (ctypes.c_int64 * 3)(*self.oN), (ctypes.c_int64 * 3)(*self.tile)
+        padded = ctypes.c_int64()
+        lib.grid_tile_rank(s, grid3, tile3, None, None, ctypes.byref(padded))
+        kp = self.kp = int(padded.value)
+        i32 = np.dtype('int32')
+        colrank = B.empty_array((self.on,), i32)
+        self.rowmap = B.empty_array((kp,), i32, name='G.H.rowmap')
+        lib.grid_tile_rank(s, grid3, tile3, colrank.ptr, self.rowmap.ptr, ctypes.byref(padded))
+        self.t_ptr = B.empty_array((kp + 1,), i32, name='G.H.rowPtrs')
+        self.t_ind = B.empty_array((max(self.nnz, 1),), i32, name='G.H.colInds')
+        self.t_val = B.empty_array((max(self.nnz, 1),), _C64, name='G.H.data')
+        work = B.empty_array((kp + 1,), i32)
+        lib.csr_transpose_conj(s, self.M, kp, self.nnz, self.G.values.ptr, self.G.colInds.ptr, self.G.rowPtrs.ptr,
+                               self.t_val.ptr, self.t_ind.ptr, self.t_ptr.ptr, work.ptr, colrank.ptr)
+        del colrank, work
+        self.grid = B.empty_array((self.on * C,), _C64, name='grid[z][y][x][c]')
+        self.ksp = B.empty_array((self.M * C,), _C64, name='ksp[m][c]')
+        if C > 32:
+            raise RuntimeError("fused SENSE path serves at most 32 coils per operator; shard or split the coils")
+
+    def __del__(self):
+        try:
+            if self._plan:
+                self.B._lib.sense_plan_destroy(self._plan)
+        except Exception:
+            pass
+
+    # ---- the four fused steps ---------------------------------------------------------------
+    def expand_fft(self, x):
+        self.B._lib.sense_expand_fft(self._plan, self.B._stream, self.grid.ptr, x.ptr, self.pf.ptr)
+
+    def grid_to_samples(self, alpha=1.0):
+        a = complex(alpha)
+        G = self.G
+        self.B._lib.ccsrmm_il(self.B._stream, self.M, self.on, self.C, self.nnz, a.real, a.imag, G.values.ptr,
+                              G.colInds.ptr, G.rowPtrs.ptr, self.grid.ptr, self.C, self.ksp.ptr, self.C, None, 0)
+
+    def samples_to_grid(self):
+        self.B._lib.ccsrmm_il(self.B._stream, self.kp, self.M, self.C, self.nnz, 1.0, 0.0, self.t_val.ptr,
+                              self.t_ind.ptr, self.t_ptr.ptr, self.ksp.ptr, self.C, self.grid.ptr, self.C,
+                              self.rowmap.ptr, 1)
+
+    def ifft_combine(self, y, alpha=1.0, beta=0.0):
+        a, b = complex(alpha), complex(beta)
+        self.B._lib.sense_ifft_combine(self._plan, self.B._stream, y.ptr, self.grid.ptr, self.pf.ptr,
+                                       a.real, a.imag, b.real, b.imag)
+
+
+def make_fused_classes(ops):
+    """Fused node classes on top of the operator family `ops` (indigo_b200.host.optree or the
+    reference's indigo.operators)."""
+
+    class FusedSenseNUFFT(ops.Operator):
+        """A = KronI(C, G' F) P : image (nvox) -> multi-coil k-space (M*C), and its adjoint."""
+
+        def __init__(self, backend, dev, name='SENSE1.fused'):
+            ops.Operator.__init__(self, backend, name=name)
+            self._dev = dev
+
+        shape = property(lambda self: (self._dev.M * self._dev.C, self._dev.nvox))
+        dtype = property(lambda self: _C64)
+
+        def _mem_usage(self, ncols=1):
+            return 0
+
+        def _eval(self, y, x, alpha=1, beta=0, forward=True, left=True):
+            if not left:
+                raise NotImplementedError("Right-multiplication not implemented for FusedSenseNUFFT.")
+            assert x.shape[1] == 1, "fused SENSE operator takes one image / one multi-coil data set at a time"
+            d, B = self._dev, self._backend
+            lib, s = B._lib, B._stream
+            b = complex(beta)
+            if forward:
+                d.expand_fft(x)
+                d.grid_to_samples(alpha)
+                lib.deinterleave(s, d.M, d.C, d.ksp.ptr, d.C, b.real, b.imag, y.ptr, d.M)
+            else:
+                lib.interleave(s, d.M, d.C, x.ptr, d.M, d.ksp.ptr, d.C)
+                d.samples_to_grid()
+                d.ifft_combine(y, alpha, beta)
+
+        @property
+        def normal(self):
+            return FusedSenseNormal(self._backend, self._dev)
+
+    class FusedSenseNormal(ops.Operator):
+        """A^H A : image -> image; k-space stays coil-interleaved between the two gathers."""
+
+        def __init__(self, backend, dev, name='SENSE.fused'):
+            ops.Operator.__init__(self, backend, name=name)
+            self._dev = dev
+
+        shape = property(lambda self: (self._dev.nvox, self._dev.nvox))
+        dtype = property(lambda self: _C64)
+
+        def _mem_usage(self, ncols=1):
+            return 0
+
+        def _eval(self, y, x, alpha=1, beta=0, forward=True, left=True):
+            if not left:
+                raise NotImplementedError("Right-multiplication not implemented for FusedSenseNormal.")
+            assert x.shape[1] == 1
+            d = self._dev
+            d.expand_fft(x)
+            d.grid_to_samples()
+            d.samples_to_grid()
+            d.ifft_combine(y, alpha, beta)
+
+    return FusedSenseNUFFT, FusedSenseNormal
+
+
+_cache = {}
+
+
+def sense_operator_fused(B, N, coord, maps, oversamp=2.0, weights=None, width=3, n=128):
+    """The SENSE operator of examples/pics.py:92-95 as one fused node (same arguments as
+    indigo_b200.sense.sense_operator).  Raises RuntimeError when the oversampled grid has no
+    specialised FFT passes; callers then fall back to sense_operator_device / sense_operator."""
+    ops = B.ops if getattr(B, 'ops', None) is not None else None
+    if ops is None:
+        import indigo.operators as ops
+    if ops not in _cache:
+        _cache[ops] = make_fused_classes(ops)
+    Fwd, _ = _cache[ops]
+    dev = SenseDevice(B, N, coord, maps, oversamp, weights, width, n)
+    return Fwd(B, dev)

@@ -53,6 +53,8 @@ def default_recipe(B, level=3):
 def normal_operator(A):
     """A^H A (the north-star apply).  lamda is passed to cg(lamda=...), never folded
     in as a Sum: under coil sharding a Sum would add it once per rank."""
+    if hasattr(A, 'normal'):              # fused node (indigo_b200.fused): k-space never leaves the interleaved layout
+        return A.normal
     AHA = A.H * A
     AHA._name = 'SENSE'
     # The arena reserved by A.optimize() is sized for A alone (transforms.py:72-76); A^H A nests one
@@ -109,31 +111,22 @@ class DeviceBuiltSpMatrix(object):
     the problem description instead of being uploaded from a scipy matrix."""
 
 
-def sense_operator_device(B, N, coord, maps, oversamp=2.0, weights=None, width=3, n=128):
-    """Same operator, same -O3 tree shape and the same six backend calls per A^H A as
-    sense_operator(), but G' and P^H are built on the GPU (ib200_kb_* / ib200_sense_ph_*)
-    straight into device CSR arrays: no COO triplets, no scipy products, no 10 GB upload.
-    Needed at BASELINE.json's full sizes (416^3 grid, 6.8 M samples: 853 M stored entries).
-    tests/test_gpu_sense.py checks structure (bit-identical) and values against the
-    host-built matrices."""
+def gridding_matrix_device(B, N, coord, oversamp=2.0, weights=None, width=3, n=128):
+    """G' = interp * (mod * scale) built on the GPU straight into device CSR arrays
+    (ib200_kb_count -> exclusive scan -> ib200_kb_fill).  Returns (csr, oN, omin, beta)."""
     import ctypes
     from scipy.signal.windows import kaiser
-    from .host.noncart import rolloff3
-    from .host import optree as op
 
     lib, s = B._lib, B._stream
     N = tuple(int(v) for v in N)
-    C = int(maps.shape[3])
     if isinstance(oversamp, tuple):
         omin, os3 = min(oversamp), oversamp
     else:
         omin, os3 = oversamp, (oversamp,) * 3
     oN = tuple(int(a * o) for a, o in zip(N, os3))
-    on, nvox = int(np.prod(oN)), int(np.prod(N))
+    on = int(np.prod(oN))
     beta = np.pi * np.sqrt(((width * 2. / omin) * (omin - 0.5)) ** 2 - 0.8)
     table = np.ascontiguousarray(kaiser(2 * n + 1, beta)[n:], dtype=np.float64)
-
-    # ---- G' = interp * (mod * scale) -------------------------------------------------
     coord = np.asarray(coord)
     c3 = np.asfortranarray(coord.reshape((3, -1), order='F').astype(np.float64))
     m = c3.shape[1]
@@ -156,6 +149,28 @@ def sense_operator_device(B, N, coord, maps, oversamp=2.0, weights=None, width=3
     B.barrier()
     del colscale_d, coord_d, counts
     Gd = B.csr_matrix.from_device(B, (m, on), g_ptr, g_ind[0:nnz], g_val[0:nnz], name='interp*mod*scale')
+    return Gd, oN, omin, beta
+
+
+def sense_operator_device(B, N, coord, maps, oversamp=2.0, weights=None, width=3, n=128):
+    """Same operator, same -O3 tree shape and the same six backend calls per A^H A as
+    sense_operator(), but G' and P^H are built on the GPU (ib200_kb_* / ib200_sense_ph_*)
+    straight into device CSR arrays: no COO triplets, no scipy products, no 10 GB upload.
+    Needed at BASELINE.json's full sizes (416^3 grid, 6.8 M samples: 853 M stored entries).
+    tests/test_gpu_sense.py checks structure (bit-identical) and values against the
+    host-built matrices."""
+    import ctypes
+    from scipy.signal.windows import kaiser
+    from .host.noncart import rolloff3
+    from .host import optree as op
+
+    lib, s = B._lib, B._stream
+    N = tuple(int(v) for v in N)
+    C = int(maps.shape[3])
+    Gd, oN, omin, beta = gridding_matrix_device(B, N, coord, oversamp, weights, width, n)
+    on, nvox = int(np.prod(oN)), int(np.prod(N))
+    from .host.noncart import rolloff3
+    from .host import optree as op
 
     # ---- P^H, stored adjoint of kron(I_C, mod*zpad*apod) * vstack(maps) ----------------
     cut = tuple(slice(a // 2 + int(np.ceil(-b / 2)), a // 2 + int(np.ceil(b / 2))) for a, b in zip(oN, N))

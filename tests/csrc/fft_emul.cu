@@ -4,6 +4,7 @@
 // sequencing and diagonal fusion can be verified in the GPU-less container.
 // The product never links this file.
 #include "../../indigo_b200/csrc/fft_plan.hpp"
+#include "../../indigo_b200/csrc/fft_il.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -68,4 +69,75 @@ extern "C" int emul_fft(int ndim, const int64_t *dims, int64_t batch, float *y, 
         for (int64_t i = 0; i < 2 * total; ++i) y[i] = x[i];
     }
     return 0;
+}
+
+
+// ---- fused SENSE transforms on the interleaved grid (fft_il.cuh + windowed strided passes) ----
+// Mirrors ib200_sense_expand_fft / ib200_sense_ifft_combine of fft.cu pass by pass.
+static int emul_strided(const AxisPlan &ax, c64 *base, int64_t inner, int64_t outer, int64_t outer_stride, int in0,
+                        int in1, int out0, int out1, int swap_in, int swap_out) {
+    FftKernelArgs k;
+    k.x = base; k.y = base; k.tw = ax.tw_dev; k.din = k.dout = nullptr; k.conj_in = k.conj_out = 0;
+    k.plane = 0; k.n = ax.n; k.L = kSpecL; k.log2L = 4; k.swap_in = swap_in; k.swap_out = swap_out;
+    k.load_first = 0; k.store_last = 0; k.st = ax.st;
+    k.in0 = in0; k.in1 = in1; k.out0 = out0; k.out1 = out1;
+    k.inner = inner; k.outer = outer; k.outer_stride = outer_stride;
+    bool done = false;
+#define EMUL_SP(n, r0, r1, r2)                                                                     \
+    if (!done && fft_spec_matches(k, n, r0, r1, r2)) {                                             \
+        done = true;                                                                               \
+        std::vector<c64> sp((size_t)2 * n * kSpecLP + 1);                                          \
+        const int64_t nb = ceil_div(k.inner, kSpecL) * k.outer;                                    \
+        for (int64_t b = 0; b < nb; ++b) fft_pass_body_spec<n, r0, r1, r2, false>(k, sp.data(), b, 0, 1); \
+    }
+    IB200_FFT_SPEC_LIST(EMUL_SP)
+#undef EMUL_SP
+    return done ? 0 : IB200_E_UNSUPPORTED;
+}
+
+extern "C" int emul_sense(const int64_t *N, const int64_t *oN, int64_t C, int which, float *grid, float *img,
+                          const float *pf, float ar, float ai, float br, float bi) {
+    FftPlanData pl;
+    int rc = fft_plan_init(&pl, 3, oN, C);
+    if (rc) return rc;
+    std::vector<std::vector<c64>> tw(3);
+    for (int a = 0; a < 3; ++a) { fft_make_twiddles(pl.ax[a].n, tw[a]); pl.ax[a].tw_dev = tw[a].data(); }
+    int64_t off[3];
+    for (int d = 0; d < 3; ++d) off[d] = oN[d] / 2 - N[d] / 2;
+    SenseFftArgs a;
+    a.N0 = (int)N[0]; a.N1 = (int)N[1]; a.N2 = (int)N[2]; a.n0 = (int)oN[0]; a.n1 = (int)oN[1]; a.n2 = (int)oN[2];
+    a.off0 = (int)off[0]; a.off1 = (int)off[1]; a.off2 = (int)off[2]; a.C = (int)C; a.tw = pl.ax[0].tw_dev;
+    a.img = (const c64 *)img; a.img_out = (c64 *)img; a.pf = (const c64 *)pf; a.grid = (c64 *)grid;
+    a.alpha = mk(ar, ai); a.beta = mk(br, bi); a.beta_zero = (br == 0.f && bi == 0.f) ? 1 : 0;
+    const int64_t sy = oN[0] * C, sz = sy * oN[1];
+    FftKernelArgs k0; k0.n = a.n0; k0.st = pl.ax[0].st;
+    bool done = false;
+    if (which == 0) {            // expand + forward FFT
+#define EMUL_X(n, r0, r1, r2)                                                                      \
+        if (!done && fft_spec_matches(k0, n, r0, r1, r2)) {                                        \
+            done = true;                                                                           \
+            std::vector<c64> sp((size_t)2 * n * kSpecLP + 1);                                      \
+            for (int64_t b = 0; b < N[1] * N[2]; ++b) sense_expand_body<n, r0, r1, r2>(a, sp.data(), b, 0, 1); \
+        }
+        IB200_FFT_SPEC_LIST(EMUL_X)
+#undef EMUL_X
+        if (!done) return IB200_E_UNSUPPORTED;
+        rc = emul_strided(pl.ax[1], (c64 *)grid + off[2] * sz, sy, N[2], sz, (int)off[1], (int)(off[1] + N[1]), 0, (int)oN[1], 0, 0);
+        if (rc) return rc;
+        return emul_strided(pl.ax[2], (c64 *)grid, sz, 1, sz * oN[2], (int)off[2], (int)(off[2] + N[2]), 0, (int)oN[2], 0, 0);
+    }
+    // inverse FFT + combine
+    rc = emul_strided(pl.ax[2], (c64 *)grid, sz, 1, sz * oN[2], 0, (int)oN[2], (int)off[2], (int)(off[2] + N[2]), 1, 0);
+    if (rc) return rc;
+    rc = emul_strided(pl.ax[1], (c64 *)grid + off[2] * sz, sy, N[2], sz, 0, (int)oN[1], (int)off[1], (int)(off[1] + N[1]), 0, 0);
+    if (rc) return rc;
+#define EMUL_C(n, r0, r1, r2)                                                                      \
+    if (!done && fft_spec_matches(k0, n, r0, r1, r2)) {                                            \
+        done = true;                                                                               \
+        std::vector<c64> sp((size_t)2 * n * kSpecLP + 1), acc((size_t)N[0] + 1);                   \
+        for (int64_t b = 0; b < N[1] * N[2]; ++b) sense_combine_body<n, r0, r1, r2>(a, sp.data(), acc.data(), b, 0, 1); \
+    }
+    IB200_FFT_SPEC_LIST(EMUL_C)
+#undef EMUL_C
+    return done ? 0 : IB200_E_UNSUPPORTED;
 }

@@ -64,3 +64,62 @@ def test_fused_diagonals(emul):
     assert rel(emul(x, -1, d1, d2, 0, 1), want) < 3e-7
     want = d2[..., None] * np.fft.ifftn(np.conj(d1)[..., None] * x128, axes=(0, 1, 2)) * np.prod(shp[:-1])
     assert rel(emul(x, +1, d1, d2, 1, 0), want) < 3e-7
+
+
+# --------------------------------------------------------------------------- fused SENSE transforms
+@pytest.fixture(scope="module")
+def emul_sense():
+    if not os.path.exists(SO):
+        import __graft_entry__ as g
+        g.build_test_helpers()
+    lib = ctypes.CDLL(SO)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    i64 = lambda v: np.array(v, dtype=np.int64)
+
+    def run(which, N, oN, C, grid, img, pf, alpha=1.0, beta=0.0):
+        a, b = complex(alpha), complex(beta)
+        n, on = i64(N), i64(oN)
+        rc = lib.emul_sense(p(n), p(on), ctypes.c_int64(C), which, p(grid), p(img), p(pf),
+                            ctypes.c_float(a.real), ctypes.c_float(a.imag), ctypes.c_float(b.real), ctypes.c_float(b.imag))
+        assert rc == 0
+    return run
+
+
+def _crand(rs, *shape):
+    return (rs.rand(*shape) + 1j * rs.rand(*shape)).astype(np.complex64)
+
+
+@pytest.mark.parametrize("N,oN,C", [((16, 16, 16), (32, 32, 32), 16), ((16, 26, 16), (32, 52, 32), 4),
+                                    ((13, 20, 16), (32, 32, 52), 20), ((32, 16, 26), (64, 32, 52), 3)])
+def test_fused_sense_expand_and_combine(emul_sense, N, oN, C):
+    """grid[z][y][x][c] = FFT3(zpad(pf*img)) and img = alpha*sum_c conj(pf)*crop(IFFT3_unscaled(grid)) + beta*img,
+    against numpy on the same data (zero-pad placement of Backend.Zpad 'center', backend.py:371-387)."""
+    rs = np.random.RandomState(sum(N) + C)
+    img = _crand(rs, *N)                                   # indexed [x, y, z]
+    pf = _crand(rs, *N, C)                                 # [x, y, z, c]
+    off = [o // 2 - n // 2 for n, o in zip(N, oN)]
+    sl = tuple(slice(o, o + n) for o, n in zip(off, N))
+    pad = np.zeros(tuple(oN) + (C,), dtype=np.complex128)
+    pad[sl] = (pf * img[..., None]).astype(np.complex128)
+    want = np.fft.fftn(pad, axes=(0, 1, 2))                # [x, y, z, c]
+    # device layouts: image x fastest; pf [voxel][coil]; grid [z][y][x][c]
+    img_d = np.ascontiguousarray(img.transpose(2, 1, 0))
+    pf_d = np.ascontiguousarray(pf.transpose(2, 1, 0, 3))
+    grid = np.full((oN[2], oN[1], oN[0], C), np.nan + 0j, dtype=np.complex64)      # every point must be written
+    emul_sense(0, N, oN, C, grid, img_d, pf_d)
+    got = grid.transpose(2, 1, 0, 3)
+    assert rel(got, want) < 5e-7
+    # inverse + combine on an arbitrary grid
+    g = _crand(rs, *oN, C)
+    grid = np.ascontiguousarray(g.transpose(2, 1, 0, 3))
+    inv = np.fft.ifftn(g.astype(np.complex128), axes=(0, 1, 2)) * np.prod(oN)
+    y0 = _crand(rs, *N)
+    alpha, beta = 0.5 - 0.25j, 1.5 + 0.5j
+    want = alpha * (np.conj(pf) * inv[sl]).sum(axis=3) + beta * y0
+    y_d = np.ascontiguousarray(y0.transpose(2, 1, 0))
+    emul_sense(1, N, oN, C, grid, y_d, pf_d, alpha, beta)
+    assert rel(y_d.transpose(2, 1, 0), want) < 5e-7
+    y_d = np.full(N[::-1], np.nan + 0j, dtype=np.complex64)                        # beta == 0 never reads img
+    grid = np.ascontiguousarray(g.transpose(2, 1, 0, 3))
+    emul_sense(1, N, oN, C, grid, y_d, pf_d, 1.0, 0.0)
+    assert rel(y_d.transpose(2, 1, 0), (np.conj(pf) * inv[sl]).sum(axis=3)) < 5e-7

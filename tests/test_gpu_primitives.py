@@ -27,6 +27,16 @@ def B():
     return B200Backend(0)
 
 
+@pytest.fixture(params=["direct", "interleaved"])
+def il(request, B):
+    """Runs a CSR test twice: with the column-major gather kernels and with the
+    coil-interleaved path (csrmm_il.cu) forced for every multi-column product."""
+    old = B.il_min_work
+    B.il_min_work = 0 if request.param == "interleaved" else (1 << 62)
+    yield request.param
+    B.il_min_work = old
+
+
 def relerr(a, b):
     a = np.asarray(a).ravel(order='F'); b = np.asarray(b).ravel(order='F')
     return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
@@ -133,7 +143,7 @@ def _rand_csr(rs, m, n, density):
 
 
 @pytest.mark.parametrize("M,N,Kc,density", list(product([23, 45], [45, 23], [1, 8, 9, 17], [0.01, 0.1, 0.5])))
-def test_csr_matrix(B, M, N, Kc, density):
+def test_csr_matrix(B, M, N, Kc, density, il):
     rs = np.random.RandomState(M * N + Kc)
     A = _rand_csr(rs, M, N, density)
     Ad = B.csr_matrix(B, A)
@@ -155,7 +165,7 @@ def test_csr_matrix(B, M, N, Kc, density):
 
 
 @pytest.mark.parametrize("M,N,Kc,alpha,beta", list(product([23, 45], [1, 8, 9, 17], [18, 19], [0.0, 0.5, 1.5], [0.0, 1.0, 1.5])))
-def test_exw_csr_matrix(B, M, N, Kc, alpha, beta):
+def test_exw_csr_matrix(B, M, N, Kc, alpha, beta, il):
     rs = np.random.RandomState(M + N + Kc)
     counts = rs.randint(0, 2, Kc)
     ptr = np.concatenate([[0], np.cumsum(counts)])
@@ -174,7 +184,7 @@ def test_exw_csr_matrix(B, M, N, Kc, alpha, beta):
     np.testing.assert_allclose(yd.to_host(), beta * y + alpha * (A.conj().T @ x), atol=1e-5)
 
 
-def test_csr_golden_leading_dims(B, golden_dir):
+def test_csr_golden_leading_dims(B, golden_dir, il):
     g = np.load(os.path.join(golden_dir, "primitives.npz"))
     m, k = (int(v) for v in g["csr_shape"])
     A = spp.csr_matrix((g["csr_data"], g["csr_indices"], g["csr_indptr"]), shape=(m, k))
@@ -196,7 +206,7 @@ def test_csr_golden_leading_dims(B, golden_dir):
     assert relerr(yd.to_host(), g["exw_adj_out"]) < 1e-6
 
 
-def test_csr_beta_zero_ignores_nan_in_y(B):
+def test_csr_beta_zero_ignores_nan_in_y(B, il):
     rs = np.random.RandomState(4)
     A = _rand_csr(rs, 200, 300, 0.05)
     Ad = B.csr_matrix(B, A)
@@ -214,7 +224,7 @@ def test_csr_beta_zero_ignores_nan_in_y(B):
 
 
 @pytest.mark.parametrize("nnz_row,ncols", [(16, 1), (32, 8), (64, 3)])
-def test_csr_sweep_shape_adjointness(B, nnz_row, ncols):
+def test_csr_sweep_shape_adjointness(B, nnz_row, ncols, il):
     """cfg2-style matrix (reduced rows) -- size-independent property <Ax,y> = <x,A^H y>
     plus a seeded oracle check on a row block."""
     rs = np.random.RandomState(nnz_row)
