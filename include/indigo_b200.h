@@ -113,7 +113,19 @@ int ib200_deinterleave(void *stream, int64_t rows, int64_t ncols, const void *Yi
 int ib200_ccsrmm_il(void *stream, int64_t m, int64_t k, int64_t ncols, int64_t nnz, float alpha_re, float alpha_im,
                     const void *vals, const int32_t *colind, const int32_t *rowptr,
                     const void *Xil, int64_t xpitch, void *Yil, int64_t ypitch,
-                    const int32_t *rowmap, int rows_per_group);
+                    const int32_t *rowmap, int rows_per_group,
+                    const int32_t *longrows, int nlong, int long_thresh);
+/* Real-weight form of the same product for matrices whose values are real (gridding matrices on
+ * grids whose extents are multiples of four: the centring phase is +-1).  ib200_csr_pack_real
+ * writes packed[p] = {int32 colind[p], float Re vals[p]} (8 bytes per entry) and returns
+ * host_max = {max |Re|, max |Im|} so that the caller can decide whether dropping the imaginary
+ * parts is admissible (synchronises).  ib200_ccsrmm_ilr is ib200_ccsrmm_il on packed entries. */
+int ib200_csr_pack_real(void *stream, int64_t nnz, const void *vals, const int32_t *colind, void *packed,
+                        float host_max[2]);
+int ib200_ccsrmm_ilr(void *stream, int64_t m, int64_t k, int64_t ncols, int64_t nnz, float alpha_re, float alpha_im,
+                     const void *packed, const int32_t *rowptr, const void *Xil, int64_t xpitch,
+                     void *Yil, int64_t ypitch, const int32_t *rowmap, int rows_per_group,
+                     const int32_t *longrows, int nlong, int long_thresh);
 /* rowmap (optional, m int32): row r of the matrix is written to output row rowmap[r]; negative
  * entries are padding rows and write nothing.  rows_per_group: consecutive-row blocking factor of
  * the kernel (0 = automatic).  Both exist for matrices whose rows were stored in tile-major
@@ -121,6 +133,13 @@ int ib200_ccsrmm_il(void *stream, int64_t m, int64_t k, int64_t ncols, int64_t n
  * ib200_grid_tile_rank fills colrank[g] = padded tile-major rank of grid point g (x fastest)
  * and rowmap[rank] = g (or -1 for padding); *padded_rows = number of ranks.  Pass NULL for both
  * arrays to query the size only. */
+/* Rows with more than long_thresh entries (the k-space centre of a radial trajectory puts ~80 000
+ * entries into single rows of the stored adjoint) are listed once by ib200_csr_long_rows
+ * (count returned through *host_count; call with capacity 0 to size the list; synchronises) and
+ * passed to the two products above as longrows[nlong]: each such row is then served by a whole
+ * CTA instead of one lane group.  nlong == 0 disables the split. */
+int ib200_csr_long_rows(void *stream, int64_t m, const int32_t *rowptr, int thresh, int32_t *list, int capacity,
+                        int *host_count);
 int ib200_grid_tile_rank(void *stream, const int64_t grid[3], const int64_t tile[3], int32_t *colrank, int32_t *rowmap,
                          int64_t *padded_rows);
 /* The inspector of _customcpu.c:179-215 on the device: out = {rows with >=1

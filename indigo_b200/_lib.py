@@ -36,7 +36,12 @@ SIGNATURES = {
     "ib200_ccsrmm": (_i, [_vp, _i, _i, _i64, _i64, _i64, _i64, _f, _f, _vp, _vp, _vp, _vp, _i64, _f, _f, _vp, _i64]),
     "ib200_interleave": (_i, [_vp, _i64, _i64, _vp, _i64, _vp, _i64]),
     "ib200_deinterleave": (_i, [_vp, _i64, _i64, _vp, _i64, _f, _f, _vp, _i64]),
-    "ib200_ccsrmm_il": (_i, [_vp, _i64, _i64, _i64, _i64, _f, _f, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i]),
+    "ib200_ccsrmm_il": (_i, [_vp, _i64, _i64, _i64, _i64, _f, _f, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i,
+                             _vp, _i, _i]),
+    "ib200_csr_long_rows": (_i, [_vp, _i64, _vp, _i, _vp, _i, POINTER(_i)]),
+    "ib200_csr_pack_real": (_i, [_vp, _i64, _vp, _vp, _vp, POINTER(c_float)]),
+    "ib200_ccsrmm_ilr": (_i, [_vp, _i64, _i64, _i64, _i64, _f, _f, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i,
+                              _vp, _i, _i]),
     "ib200_grid_tile_rank": (_i, [_vp, POINTER(_i64), POINTER(_i64), _vp, _vp, POINTER(_i64)]),
     "ib200_csr_inspect": (_i, [_vp, _i64, _i64, _vp, _vp, _vp, POINTER(_i64)]),
     "ib200_csr_transpose_conj": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -376,7 +376,7 @@ def make_backend_class(Base, name="B200Backend"):
                 yil = self._il_scratch('y', m * ncols)
                 self._lib.interleave(s, k, ncols, x.ptr, x.ld, xil, ncols)
                 self._lib.ccsrmm_il(s, m, k, ncols, nnz, ar, ai, A_vals.ptr, A_indx.ptr, A_ptr.ptr, xil, ncols, yil, ncols,
-                                    None, 0)
+                                    None, 0, None, 0, 0)
                 self._lib.deinterleave(s, m, ncols, yil, ncols, br, bi, y.ptr, y.ld)
                 return
             self._lib.ccsrmm(self._stream, 1 if adjoint else 0, 1 if exwrite else 0, m, k, ncols,

@@ -20,6 +20,8 @@
 // (rows = grid points, 0..2400 entries), so no atomics are needed anywhere.
 #include "common.cuh"
 
+#include <cstring>
+
 namespace ib200 {
 
 // ---------------------------------------------------------------------------
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(256) csrmm_il_kernel(int64_t m, int C, c64 alp
                                                        const int32_t *__restrict__ rowptr,
                                                        const c64 *__restrict__ Xil, uint32_t xpitch_bytes,
                                                        c64 *__restrict__ Yil, int64_t ypitch,
-                                                       const int32_t *__restrict__ rowmap, int rpg) {
+                                                       const int32_t *__restrict__ rowmap, int rpg, int long_thresh) {
     constexpr int NP = GL / CL, GPB = 256 / GL;
     constexpr int U = CL >= 4 ? 4 : CL;                             // loads issued back to back
     constexpr unsigned FULL = 0xffffffffu;
@@ -110,6 +112,8 @@ __global__ void __launch_bounds__(256) csrmm_il_kernel(int64_t m, int C, c64 alp
         const int64_t row = row0 + (int64_t)i * GPB;
         int p0 = 0, len = 0;
         if (row < m) { p0 = __ldg(rowptr + row); len = __ldg(rowptr + row + 1) - p0; }
+        const bool is_long = len > long_thresh;                     // left to csrmm_il_long_kernel
+        if (is_long) len = 0;
         int maxlen = len;
 #pragma unroll
         for (int o = GL; o < 32; o <<= 1) { const int t = __shfl_xor_sync(FULL, maxlen, o); maxlen = t > maxlen ? t : maxlen; }
@@ -170,7 +174,79 @@ __global__ void __launch_bounds__(256) csrmm_il_kernel(int64_t m, int C, c64 alp
             acc.x += __shfl_xor_sync(FULL, acc.x, o, GL);
             acc.y += __shfl_xor_sync(FULL, acc.y, o, GL);
         }
-        if (row < m && slot == 0 && coil < C) {
+        if (row < m && slot == 0 && coil < C && !is_long) {
+            const int64_t out = rowmap ? (int64_t)__ldg(rowmap + row) : row;
+            if (out >= 0) __stcs(Yil + out * ypitch + coil, cmul(alpha, acc));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Real-weight variant: entries are packed (column, weight) pairs of 8 bytes.
+// Gridding matrices are real up to the centring phase, which is +-1 on grids whose extents are
+// multiples of four, so two thirds of the matrix bytes and half of the multiplies suffice.
+// Every lane fetches its entry itself: the CL lanes of an entry read the same 8 bytes (one
+// broadcast request), which removes the batch load + shuffle hand-out of the complex kernel and
+// all of its per-row bookkeeping -- what matters for the stored adjoint, whose rows hold 12
+// entries on average.  Entries of one row are consumed four at a time (independent loads).
+struct __align__(8) PackedEntry { int32_t col; float w; };
+
+__device__ __forceinline__ PackedEntry ld_entry(const PackedEntry *p) {
+    const int2 v = __ldg(reinterpret_cast<const int2 *>(p));
+    PackedEntry e; e.col = v.x; e.w = __int_as_float(v.y);
+    return e;
+}
+
+template <int GL, int CL>
+__global__ void __launch_bounds__(256) csrmm_ilr_kernel(int64_t m, int C, c64 alpha,
+                                                        const PackedEntry *__restrict__ ent,
+                                                        const int32_t *__restrict__ rowptr,
+                                                        const c64 *__restrict__ Xil, uint32_t xpitch_bytes,
+                                                        c64 *__restrict__ Yil, int64_t ypitch,
+                                                        const int32_t *__restrict__ rowmap, int rpg, int long_thresh) {
+    constexpr int NP = GL / CL, GPB = 256 / GL;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int gl = (int)(threadIdx.x & (GL - 1));
+    const int coil = gl & (CL - 1);
+    const int slot = gl / CL;
+    const int group = (int)(threadIdx.x / GL);
+    const char *xb = reinterpret_cast<const char *>(Xil + (coil < C ? coil : 0));
+    const int64_t row0 = (int64_t)blockIdx.x * ((int64_t)GPB * rpg) + group;
+    for (int i = 0; i < rpg; ++i) {
+        const int64_t row = row0 + (int64_t)i * GPB;
+        int p = 0, p1 = 0;
+        if (row < m) { p = __ldg(rowptr + row); p1 = __ldg(rowptr + row + 1); }
+        const bool is_long = p1 - p > long_thresh;                  // left to csrmm_il_long_kernel
+        if (is_long) p1 = p;
+        p += slot;
+        float ax = 0.f, ay = 0.f, bx = 0.f, by = 0.f;
+        for (; p + 3 * NP < p1; p += 4 * NP) {
+            const PackedEntry e0 = ld_entry(ent + p), e1 = ld_entry(ent + p + NP), e2 = ld_entry(ent + p + 2 * NP),
+                              e3 = ld_entry(ent + p + 3 * NP);
+            const c64 x0 = __ldg(reinterpret_cast<const c64 *>(xb + (uint64_t)(uint32_t)e0.col * xpitch_bytes));
+            const c64 x1 = __ldg(reinterpret_cast<const c64 *>(xb + (uint64_t)(uint32_t)e1.col * xpitch_bytes));
+            const c64 x2 = __ldg(reinterpret_cast<const c64 *>(xb + (uint64_t)(uint32_t)e2.col * xpitch_bytes));
+            const c64 x3 = __ldg(reinterpret_cast<const c64 *>(xb + (uint64_t)(uint32_t)e3.col * xpitch_bytes));
+            ax = fmaf(e0.w, x0.x, ax); ay = fmaf(e0.w, x0.y, ay);
+            bx = fmaf(e1.w, x1.x, bx); by = fmaf(e1.w, x1.y, by);
+            ax = fmaf(e2.w, x2.x, ax); ay = fmaf(e2.w, x2.y, ay);
+            bx = fmaf(e3.w, x3.x, bx); by = fmaf(e3.w, x3.y, by);
+        }
+        for (; p < p1; p += NP) {
+            const PackedEntry e0 = ld_entry(ent + p);
+            const c64 x0 = __ldg(reinterpret_cast<const c64 *>(xb + (uint64_t)(uint32_t)e0.col * xpitch_bytes));
+            ax = fmaf(e0.w, x0.x, ax); ay = fmaf(e0.w, x0.y, ay);
+        }
+        c64 acc = mk(ax + bx, ay + by);
+        if (NP > 1) {
+            __syncwarp();
+#pragma unroll
+            for (int o = CL; o < GL; o <<= 1) {
+                acc.x += __shfl_xor_sync(FULL, acc.x, o, GL);
+                acc.y += __shfl_xor_sync(FULL, acc.y, o, GL);
+            }
+        }
+        if (row < m && slot == 0 && coil < C && !is_long) {
             const int64_t out = rowmap ? (int64_t)__ldg(rowmap + row) : row;
             if (out >= 0) __stcs(Yil + out * ypitch + coil, cmul(alpha, acc));
         }
@@ -178,15 +254,143 @@ __global__ void __launch_bounds__(256) csrmm_il_kernel(int64_t m, int C, c64 alp
 }
 
 template <int GL, int CL>
+static int launch_ilr(cudaStream_t s, int64_t m, int C, c64 alpha, const PackedEntry *ent, const int32_t *rowptr,
+                      const c64 *Xil, int64_t xpitch, c64 *Yil, int64_t ypitch, const int32_t *rowmap, int rpg,
+                      int long_thresh) {
+    const int64_t rows_per_cta = (int64_t)(256 / GL) * rpg;
+    const int64_t blocks = ceil_div(m, rows_per_cta);
+    IB200_REQUIRE(blocks < (1LL << 31), "matrix too large for one launch");
+    IB200_REQUIRE(xpitch * (int64_t)sizeof(c64) < (1LL << 32), "operand pitch too large");
+    csrmm_ilr_kernel<GL, CL><<<(unsigned)blocks, 256, 0, s>>>(m, C, alpha, ent, rowptr, Xil,
+                                                              (uint32_t)(xpitch * sizeof(c64)), Yil, ypitch, rowmap, rpg,
+                                                              long_thresh);
+    IB200_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Long rows.  The stored adjoint of a radial trajectory has a handful of enormous rows: every
+// spoke passes through the k-space centre, so the central grid points of cfg3 collect ~100 000
+// entries each while the mean is 12.  One 16-lane group walking such a row alone would take as
+// long as the rest of the matrix; rows above `long_thresh` entries are therefore skipped by the
+// kernels above and each gets a whole CTA here (256/CL entries in flight per step, shared-memory
+// fold of the partial sums, plain store).
+template <int CL, bool PACKED>
+__global__ void __launch_bounds__(256) csrmm_il_long_kernel(const int32_t *__restrict__ longrows, int C, c64 alpha,
+                                                            const PackedEntry *__restrict__ ent,
+                                                            const c64 *__restrict__ vals,
+                                                            const int32_t *__restrict__ colind,
+                                                            const int32_t *__restrict__ rowptr,
+                                                            const c64 *__restrict__ Xil, uint32_t xpitch_bytes,
+                                                            c64 *__restrict__ Yil, int64_t ypitch,
+                                                            const int32_t *__restrict__ rowmap) {
+    constexpr int NS = 256 / CL;                                    // entries in flight per step
+    __shared__ c64 part[256];
+    const int64_t row = longrows[blockIdx.x];
+    const int coil = (int)(threadIdx.x & (CL - 1));
+    const int slot = (int)(threadIdx.x / CL);
+    const char *xb = reinterpret_cast<const char *>(Xil + (coil < C ? coil : 0));
+    int p = __ldg(rowptr + row) + slot;
+    const int p1 = __ldg(rowptr + row + 1);
+    c64 a0 = mk(0.f, 0.f), a1 = mk(0.f, 0.f);
+    auto fetch = [&](int q, unsigned &col, c64 &v) {
+        if (PACKED) { const PackedEntry e = ld_entry(ent + q); col = (unsigned)e.col; v = mk(e.w, 0.f); }
+        else { col = (unsigned)__ldg(colind + q); v = __ldg(vals + q); }
+    };
+    for (; p + 3 * NS < p1; p += 4 * NS) {
+        unsigned c0, c1, c2, c3; c64 v0, v1, v2, v3;
+        fetch(p, c0, v0); fetch(p + NS, c1, v1); fetch(p + 2 * NS, c2, v2); fetch(p + 3 * NS, c3, v3);
+        const c64 x0 = __ldg(reinterpret_cast<const c64 *>(xb + (uint64_t)c0 * xpitch_bytes));
+        const c64 x1 = __ldg(reinterpret_cast<const c64 *>(xb + (uint64_t)c1 * xpitch_bytes));
+        const c64 x2 = __ldg(reinterpret_cast<const c64 *>(xb + (uint64_t)c2 * xpitch_bytes));
+        const c64 x3 = __ldg(reinterpret_cast<const c64 *>(xb + (uint64_t)c3 * xpitch_bytes));
+        if (PACKED) {
+            a0.x = fmaf(v0.x, x0.x, a0.x); a0.y = fmaf(v0.x, x0.y, a0.y);
+            a1.x = fmaf(v1.x, x1.x, a1.x); a1.y = fmaf(v1.x, x1.y, a1.y);
+            a0.x = fmaf(v2.x, x2.x, a0.x); a0.y = fmaf(v2.x, x2.y, a0.y);
+            a1.x = fmaf(v3.x, x3.x, a1.x); a1.y = fmaf(v3.x, x3.y, a1.y);
+        } else {
+            a0 = cfma(v0, x0, a0); a1 = cfma(v1, x1, a1); a0 = cfma(v2, x2, a0); a1 = cfma(v3, x3, a1);
+        }
+    }
+    for (; p < p1; p += NS) {
+        unsigned c0; c64 v0;
+        fetch(p, c0, v0);
+        const c64 x0 = __ldg(reinterpret_cast<const c64 *>(xb + (uint64_t)c0 * xpitch_bytes));
+        a0 = cfma(v0, x0, a0);
+    }
+    part[threadIdx.x] = cadd(a0, a1);
+    __syncthreads();
+    for (int h = NS / 2; h > 0; h >>= 1) {                          // fold the slots (tree order: deterministic)
+        if (slot < h) part[threadIdx.x] = cadd(part[threadIdx.x], part[threadIdx.x + h * CL]);
+        __syncthreads();
+    }
+    if (slot == 0 && coil < C) {
+        const int64_t out = rowmap ? (int64_t)__ldg(rowmap + row) : row;
+        if (out >= 0) Yil[out * ypitch + coil] = cmul(alpha, part[threadIdx.x]);
+    }
+}
+
+__global__ void __launch_bounds__(256) long_rows_kernel(int64_t m, const int32_t *__restrict__ rowptr, int thresh,
+                                                        int32_t *__restrict__ list, int capacity, int *count) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    if (rowptr[r + 1] - rowptr[r] > thresh) {
+        const int at = atomicAdd(count, 1);
+        if (at < capacity) list[at] = (int32_t)r;
+    }
+}
+
+template <bool PACKED>
+static int launch_long(cudaStream_t s, int CL, int nlong, const int32_t *longrows, int C, c64 alpha, const void *ent,
+                       const c64 *vals, const int32_t *colind, const int32_t *rowptr, const c64 *Xil, int64_t xpitch,
+                       c64 *Yil, int64_t ypitch, const int32_t *rowmap) {
+    if (nlong <= 0) return 0;
+    IB200_REQUIRE(longrows != nullptr, "long-row list missing");
+    const uint32_t pb = (uint32_t)(xpitch * sizeof(c64));
+    const PackedEntry *e = (const PackedEntry *)ent;
+#define IB200_LONG(cl) case cl: csrmm_il_long_kernel<cl, PACKED><<<(unsigned)nlong, 256, 0, s>>>(longrows, C, alpha, e, vals, colind, rowptr, Xil, pb, Yil, ypitch, rowmap); break
+    switch (CL) { IB200_LONG(1); IB200_LONG(2); IB200_LONG(4); IB200_LONG(8); IB200_LONG(16); IB200_LONG(32);
+                  default: set_error("internal: bad CL"); return IB200_E_UNSUPPORTED; }
+#undef IB200_LONG
+    IB200_LAUNCH_CHECK();
+    return 0;
+}
+
+// packed[p] = (colind[p], Re vals[p]);  stats[0] = max |Re|, stats[1] = max |Im| (as float bit patterns, >= 0)
+__global__ void __launch_bounds__(256) pack_real_kernel(int64_t nnz, const c64 *__restrict__ vals,
+                                                        const int32_t *__restrict__ colind,
+                                                        PackedEntry *__restrict__ packed, unsigned *stats) {
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    float mre = 0.f, mim = 0.f;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += nth) {
+        const c64 v = vals[p];
+        PackedEntry e; e.col = colind[p]; e.w = v.x;
+        packed[p] = e;
+        mre = fmaxf(mre, fabsf(v.x)); mim = fmaxf(mim, fabsf(v.y));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mre = fmaxf(mre, __shfl_xor_sync(0xffffffffu, mre, o));
+        mim = fmaxf(mim, __shfl_xor_sync(0xffffffffu, mim, o));
+    }
+    if ((threadIdx.x & 31) == 0) {                                // non-negative floats order like unsigned ints
+        atomicMax(stats, __float_as_uint(mre));
+        atomicMax(stats + 1, __float_as_uint(mim));
+    }
+}
+
+template <int GL, int CL>
 static int launch_il(cudaStream_t s, int64_t m, int C, c64 alpha, const c64 *vals, const int32_t *colind,
                      const int32_t *rowptr, const c64 *Xil, int64_t xpitch, c64 *Yil, int64_t ypitch,
-                     const int32_t *rowmap, int rpg) {
+                     const int32_t *rowmap, int rpg, int long_thresh) {
     const int64_t rows_per_cta = (int64_t)(256 / GL) * rpg;
     const int64_t blocks = ceil_div(m, rows_per_cta);
     IB200_REQUIRE(blocks < (1LL << 31), "matrix too large for one launch");
     IB200_REQUIRE(xpitch * (int64_t)sizeof(c64) < (1LL << 32), "operand pitch too large");
     csrmm_il_kernel<GL, CL><<<(unsigned)blocks, 256, 0, s>>>(m, C, alpha, vals, colind, rowptr, Xil,
-                                                             (uint32_t)(xpitch * sizeof(c64)), Yil, ypitch, rowmap, rpg);
+                                                             (uint32_t)(xpitch * sizeof(c64)), Yil, ypitch, rowmap, rpg,
+                                                             long_thresh);
     IB200_LAUNCH_CHECK();
     return 0;
 }
@@ -261,11 +465,13 @@ int ib200_deinterleave(void *stream, int64_t rows, int64_t ncols, const void *Yi
 
 int ib200_ccsrmm_il(void *stream, int64_t m, int64_t k, int64_t ncols, int64_t nnz, float ar, float ai,
                     const void *vals, const int32_t *colind, const int32_t *rowptr, const void *Xil, int64_t xpitch,
-                    void *Yil, int64_t ypitch, const int32_t *rowmap, int rows_per_group) {
+                    void *Yil, int64_t ypitch, const int32_t *rowmap, int rows_per_group,
+                    const int32_t *longrows, int nlong, int long_thresh) {
     IB200_REQUIRE(m >= 0 && k >= 0 && ncols >= 0 && nnz >= 0, "negative dimension");
     IB200_REQUIRE(m < (1LL << 31) && k < (1LL << 31) && nnz < (1LL << 31), "int32 CSR indices: dimensions must be < 2^31");
     IB200_REQUIRE(ncols <= 32, "interleaved SpMM serves at most 32 columns per call");
     if (m == 0 || ncols == 0) return 0;
+    if (nlong <= 0 || !longrows) { nlong = 0; long_thresh = 0x7fffffff; }
     IB200_REQUIRE(rowptr && Yil && (nnz == 0 || (vals && colind && Xil)), "null pointer");
     IB200_REQUIRE(xpitch >= ncols && ypitch >= ncols, "pitch smaller than the column count");
     IB200_REQUIRE(rows_per_group >= 0 && rows_per_group <= 4096, "rows_per_group out of range");
@@ -281,8 +487,11 @@ int ib200_ccsrmm_il(void *stream, int64_t m, int64_t k, int64_t ncols, int64_t n
     if (rpg < 1) rpg = 1;
     const c64 alpha = mk(ar, ai);
     cudaStream_t s = as_stream(stream);
+    int rc = launch_long<false>(s, CL, nlong, longrows, (int)ncols, alpha, nullptr, (const c64 *)vals, colind, rowptr,
+                                (const c64 *)Xil, xpitch, (c64 *)Yil, ypitch, rowmap);
+    if (rc) return rc;
 #define IB200_IL_CASE(gl, cl) \
-    case (gl) * 100 + (cl): return launch_il<gl, cl>(s, m, (int)ncols, alpha, (const c64 *)vals, colind, rowptr, (const c64 *)Xil, xpitch, (c64 *)Yil, ypitch, rowmap, rpg)
+    case (gl) * 100 + (cl): return launch_il<gl, cl>(s, m, (int)ncols, alpha, (const c64 *)vals, colind, rowptr, (const c64 *)Xil, xpitch, (c64 *)Yil, ypitch, rowmap, rpg, long_thresh)
     switch (GL * 100 + CL) {
         IB200_IL_CASE(1, 1);
         IB200_IL_CASE(2, 1); IB200_IL_CASE(2, 2);
@@ -315,6 +524,89 @@ int ib200_grid_tile_rank(void *stream, const int64_t grid[3], const int64_t tile
                                                                 (int)tile[1], (int)tile[2], colrank, rowmap);
     IB200_LAUNCH_CHECK();
     return 0;
+}
+
+int ib200_csr_long_rows(void *stream, int64_t m, const int32_t *rowptr, int thresh, int32_t *list, int capacity,
+                        int *host_count) {
+    IB200_REQUIRE(m >= 0 && host_count && thresh >= 0 && capacity >= 0, "bad arguments");
+    *host_count = 0;
+    if (m == 0) return 0;
+    IB200_REQUIRE(rowptr && (list || capacity == 0), "null pointer");
+    cudaStream_t s = as_stream(stream);
+    int *cnt = nullptr;
+    IB200_TRY(cudaMalloc(&cnt, sizeof(int)));
+    cudaMemsetAsync(cnt, 0, sizeof(int), s);
+    long_rows_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, s>>>(m, rowptr, thresh, list, capacity, cnt);
+    count_launch();
+    cudaMemcpyAsync(host_count, cnt, sizeof(int), cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    cudaFree(cnt);
+    IB200_TRY(e);
+    IB200_TRY(cudaGetLastError());
+    return 0;
+}
+
+int ib200_csr_pack_real(void *stream, int64_t nnz, const void *vals, const int32_t *colind, void *packed,
+                        float host_max[2]) {
+    IB200_REQUIRE(nnz >= 0 && host_max, "bad arguments");
+    host_max[0] = host_max[1] = 0.f;
+    if (nnz == 0) return 0;
+    IB200_REQUIRE(vals && colind && packed, "null pointer");
+    cudaStream_t s = as_stream(stream);
+    unsigned *stats = nullptr;
+    IB200_TRY(cudaMalloc(&stats, 2 * sizeof(unsigned)));
+    cudaMemsetAsync(stats, 0, 2 * sizeof(unsigned), s);
+    int64_t g = ceil_div(nnz, 256 * 4); const int64_t cap = (int64_t)sm_count() * 16; if (g > cap) g = cap;
+    pack_real_kernel<<<(unsigned)g, 256, 0, s>>>(nnz, (const c64 *)vals, colind, (PackedEntry *)packed, stats);
+    count_launch();
+    unsigned h[2] = {0, 0};
+    cudaMemcpyAsync(h, stats, sizeof(h), cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    cudaFree(stats);
+    IB200_TRY(e);
+    IB200_TRY(cudaGetLastError());
+    memcpy(host_max, h, sizeof(h));
+    return 0;
+}
+
+int ib200_ccsrmm_ilr(void *stream, int64_t m, int64_t k, int64_t ncols, int64_t nnz, float ar, float ai,
+                     const void *packed, const int32_t *rowptr, const void *Xil, int64_t xpitch,
+                     void *Yil, int64_t ypitch, const int32_t *rowmap, int rows_per_group,
+                     const int32_t *longrows, int nlong, int long_thresh) {
+    IB200_REQUIRE(m >= 0 && k >= 0 && ncols >= 0 && nnz >= 0, "negative dimension");
+    IB200_REQUIRE(m < (1LL << 31) && k < (1LL << 31) && nnz < (1LL << 31), "int32 CSR indices: dimensions must be < 2^31");
+    IB200_REQUIRE(ncols <= 32, "interleaved SpMM serves at most 32 columns per call");
+    if (m == 0 || ncols == 0) return 0;
+    if (nlong <= 0 || !longrows) { nlong = 0; long_thresh = 0x7fffffff; }
+    IB200_REQUIRE(rowptr && Yil && (nnz == 0 || (packed && Xil)), "null pointer");
+    IB200_REQUIRE(xpitch >= ncols && ypitch >= ncols, "pitch smaller than the column count");
+    IB200_REQUIRE(rows_per_group >= 0 && rows_per_group <= 4096, "rows_per_group out of range");
+    const int CL = pow2_ceil(ncols);
+    const double avg = (double)nnz / (double)m;
+    int GL = CL;
+    while (GL < 32 && avg >= 4.0 * GL) GL <<= 1;                 // slots only pay when each gets >= 4 entries
+    int rpg = rows_per_group;
+    if (rpg == 0) rpg = avg >= 32 ? (32 * GL) / 256 : 1;
+    if (rpg < 1) rpg = 1;
+    const c64 alpha = mk(ar, ai);
+    cudaStream_t s = as_stream(stream);
+    int rc = launch_long<true>(s, CL, nlong, longrows, (int)ncols, alpha, packed, nullptr, nullptr, rowptr,
+                               (const c64 *)Xil, xpitch, (c64 *)Yil, ypitch, rowmap);
+    if (rc) return rc;
+#define IB200_ILR_CASE(gl, cl) \
+    case (gl) * 100 + (cl): return launch_ilr<gl, cl>(s, m, (int)ncols, alpha, (const PackedEntry *)packed, rowptr, (const c64 *)Xil, xpitch, (c64 *)Yil, ypitch, rowmap, rpg, long_thresh)
+    switch (GL * 100 + CL) {
+        IB200_ILR_CASE(1, 1);
+        IB200_ILR_CASE(2, 1); IB200_ILR_CASE(2, 2);
+        IB200_ILR_CASE(4, 1); IB200_ILR_CASE(4, 2); IB200_ILR_CASE(4, 4);
+        IB200_ILR_CASE(8, 1); IB200_ILR_CASE(8, 2); IB200_ILR_CASE(8, 4); IB200_ILR_CASE(8, 8);
+        IB200_ILR_CASE(16, 1); IB200_ILR_CASE(16, 2); IB200_ILR_CASE(16, 4); IB200_ILR_CASE(16, 8); IB200_ILR_CASE(16, 16);
+        IB200_ILR_CASE(32, 1); IB200_ILR_CASE(32, 2); IB200_ILR_CASE(32, 4); IB200_ILR_CASE(32, 8); IB200_ILR_CASE(32, 16);
+        IB200_ILR_CASE(32, 32);
+    }
+#undef IB200_ILR_CASE
+    set_error("internal: no interleaved kernel for GL=%d CL=%d", GL, CL);
+    return IB200_E_UNSUPPORTED;
 }
 
 }  // extern "C"

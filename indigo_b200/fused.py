@@ -30,6 +30,8 @@ class SenseDevice(object):
     """Device-resident pieces shared by the fused nodes of one SENSE operator."""
 
     tile = (4, 4, 4)
+    allow_real = True          # use the real-weight packed kernels when the matrix values are real
+    long_thresh = 512          # rows of G'^H with more entries than this get a whole CTA each
 
     def __init__(self, B, N, coord, maps, oversamp=2.0, weights=None, width=3, n=128):
         from .sense import gridding_matrix_device, _fftc_mod
@@ -71,6 +73,26 @@ class SenseDevice(object):
         lib.csr_transpose_conj(s, self.M, kp, self.nnz, self.G.values.ptr, self.G.colInds.ptr, self.G.rowPtrs.ptr,
                                self.t_val.ptr, self.t_ind.ptr, self.t_ptr.ptr, work.ptr, colrank.ptr)
         del colrank, work
+        # real-weight packed entries (8 B instead of 12 B per stored entry, half the multiplies) when
+        # the centring phase folded into G' is real, i.e. on every grid the fused path serves
+        self.real = False
+        if self.nnz and self.allow_real:
+            pk = np.dtype('int64')                                     # 8-byte (int32 column, float32 weight) records
+            g_pk = B.empty_array((self.nnz,), pk, name='G.packed')
+            hmax = (ctypes.c_float * 2)()
+            lib.csr_pack_real(s, self.nnz, self.G.values.ptr, self.G.colInds.ptr, g_pk.ptr, hmax)
+            if hmax[1] <= 1e-8 * hmax[0]:
+                t_pk = B.empty_array((self.nnz,), pk, name='G.H.packed')
+                lib.csr_pack_real(s, self.nnz, self.t_val.ptr, self.t_ind.ptr, t_pk.ptr, hmax)
+                self.g_pk, self.t_pk, self.real = g_pk, t_pk, True
+                self.t_val = self.t_ind = None                          # the complex copy of G'^H is not needed any more
+        # rows of G'^H that are long enough to deserve a whole CTA (k-space centre of radial trajectories)
+        cnt = ctypes.c_int()
+        lib.csr_long_rows(s, kp, self.t_ptr.ptr, self.long_thresh, None, 0, ctypes.byref(cnt))
+        self.nlong, self.longrows = int(cnt.value), None
+        if self.nlong:
+            self.longrows = B.empty_array((self.nlong,), i32, name='G.H.longrows')
+            lib.csr_long_rows(s, kp, self.t_ptr.ptr, self.long_thresh, self.longrows.ptr, self.nlong, ctypes.byref(cnt))
         self.grid = B.empty_array((self.on * C,), _C64, name='grid[z][y][x][c]')
         self.ksp = B.empty_array((self.M * C,), _C64, name='ksp[m][c]')
         if C > 32:
@@ -89,14 +111,24 @@ class SenseDevice(object):
 
     def grid_to_samples(self, alpha=1.0):
         a = complex(alpha)
-        G = self.G
-        self.B._lib.ccsrmm_il(self.B._stream, self.M, self.on, self.C, self.nnz, a.real, a.imag, G.values.ptr,
-                              G.colInds.ptr, G.rowPtrs.ptr, self.grid.ptr, self.C, self.ksp.ptr, self.C, None, 0)
+        G, lib, s = self.G, self.B._lib, self.B._stream
+        if self.real:
+            lib.ccsrmm_ilr(s, self.M, self.on, self.C, self.nnz, a.real, a.imag, self.g_pk.ptr, G.rowPtrs.ptr,
+                           self.grid.ptr, self.C, self.ksp.ptr, self.C, None, 0, None, 0, 0)
+        else:
+            lib.ccsrmm_il(s, self.M, self.on, self.C, self.nnz, a.real, a.imag, G.values.ptr, G.colInds.ptr,
+                          G.rowPtrs.ptr, self.grid.ptr, self.C, self.ksp.ptr, self.C, None, 0, None, 0, 0)
 
     def samples_to_grid(self):
-        self.B._lib.ccsrmm_il(self.B._stream, self.kp, self.M, self.C, self.nnz, 1.0, 0.0, self.t_val.ptr,
-                              self.t_ind.ptr, self.t_ptr.ptr, self.ksp.ptr, self.C, self.grid.ptr, self.C,
-                              self.rowmap.ptr, 1)
+        lib, s = self.B._lib, self.B._stream
+        lr = self.longrows.ptr if self.nlong else None
+        if self.real:
+            lib.ccsrmm_ilr(s, self.kp, self.M, self.C, self.nnz, 1.0, 0.0, self.t_pk.ptr, self.t_ptr.ptr,
+                           self.ksp.ptr, self.C, self.grid.ptr, self.C, self.rowmap.ptr, 1, lr, self.nlong, self.long_thresh)
+        else:
+            lib.ccsrmm_il(s, self.kp, self.M, self.C, self.nnz, 1.0, 0.0, self.t_val.ptr, self.t_ind.ptr,
+                          self.t_ptr.ptr, self.ksp.ptr, self.C, self.grid.ptr, self.C, self.rowmap.ptr, 1,
+                          lr, self.nlong, self.long_thresh)
 
     def ifft_combine(self, y, alpha=1.0, beta=0.0):
         a, b = complex(alpha), complex(beta)

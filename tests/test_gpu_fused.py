@@ -42,10 +42,14 @@ def _setup(N, C, traj, weighted, seed=0):
     return rs, coord, maps, w
 
 
+@pytest.mark.parametrize("real", [True, False], ids=["real-packed", "complex"])
 @pytest.mark.parametrize("N,C,traj,weighted", CASES)
-def test_fused_against_oracle(B, N, C, traj, weighted):
+def test_fused_against_oracle(B, N, C, traj, weighted, real, monkeypatch):
+    from indigo_b200 import fused
+    monkeypatch.setattr(fused.SenseDevice, "allow_real", real)
     rs, coord, maps, w = _setup(N, C, traj, weighted)
     A = sense_operator_fused(B, N, coord, maps, 2.0, weights=w)
+    assert A._dev.real == real
     ref = osense.SenseOperator(N, coord, maps, 2.0, weights=w)
     nvox = int(np.prod(N))
     x = synth.rand64c(rs, nvox, 1)

@@ -3,12 +3,13 @@
 
     python tools/bench_grid.py [--workload cfg3] [--coils 16] [--reps 5]
 
-Times, with CUDA events on the launching stream, the pieces of Backend.ccsrmm for the
-Kaiser-Bessel matrix G' (forward: grid -> samples) and its stored conjugate transpose
-(adjoint: samples -> grid): interleave / gather / deinterleave.  Prints one JSON line.
-Kept short so that it can run under `ncu --set full -k regex:csrmm_il`.
+Times, with CUDA events on the launching stream, the interleaved gathers for the Kaiser-Bessel
+matrix G' (forward: grid -> samples) and its stored conjugate transpose in tile-major row order
+(adjoint: samples -> grid), complex and real-packed entries, with and without the long-row split.
+Prints one JSON line.  Short enough to run under `ncu --set full -k regex:csrmm_il`.
 """
 import argparse
+import ctypes
 import json
 import os
 import sys
@@ -30,22 +31,18 @@ def main():
     ap.add_argument("--workload", default="cfg3")
     ap.add_argument("--coils", type=int, default=0)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--thresh", type=int, default=512)
     args = ap.parse_args()
     wl = bench.WORKLOADS[args.workload]
     C = args.coils or wl["C"]
     B = B200Backend(0)
     lib, s = B._lib, B._stream
-    t0 = time.time()
     G, oN, _, _ = gridding_matrix_device(B, wl["N"], bench.make_traj(wl["traj"]), wl["oversamp"])
-    B.barrier(); t_g = time.time() - t0
-    t0 = time.time()
-    tp, ti, tv = G._stored_adjoint()
-    B.barrier(); t_t = time.time() - t0
     m, k = G.shape
     nnz = int(G.values.size)
-    xil = torch.rand(k * C * 2, device="cuda", dtype=torch.float32)
-    kil = torch.rand(m * C * 2, device="cuda", dtype=torch.float32)
-    xcm = torch.rand(k * C * 2, device="cuda", dtype=torch.float32)
+    torch.manual_seed(1)
+    xil = torch.randn(k * C * 2, device="cuda", dtype=torch.float32)
+    kil = torch.randn(m * C * 2, device="cuda", dtype=torch.float32)
 
     def timed(fn):
         fn(); torch.cuda.synchronize()
@@ -54,53 +51,64 @@ def main():
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); fn(); b.record(); torch.cuda.synchronize()
             ts.append(a.elapsed_time(b))
-        return float(np.median(ts)) if ts else 0.0
+        return round(float(np.median(ts)), 3) if ts else 0.0
 
-    out = {"workload": args.workload, "coils": C, "m": m, "k": k, "nnz": nnz, "build_G_s": round(t_g, 2),
-           "build_GH_s": round(t_t, 2)}
-    import ctypes
-    out["fwd_gather_ms"] = timed(lambda: lib.ccsrmm_il(s, m, k, C, nnz, 1.0, 0.0, G.values.ptr, G.colInds.ptr,
-                                                       G.rowPtrs.ptr, xil.data_ptr(), C, kil.data_ptr(), C, None, 0))
-    for rpg in (1, 2, 8):
-        out["fwd_gather_rpg%d_ms" % rpg] = timed(lambda: lib.ccsrmm_il(
-            s, m, k, C, nnz, 1.0, 0.0, G.values.ptr, G.colInds.ptr, G.rowPtrs.ptr, xil.data_ptr(), C, kil.data_ptr(), C,
-            None, rpg))
-    out["adj_gather_ms"] = timed(lambda: lib.ccsrmm_il(s, k, m, C, nnz, 1.0, 0.0, tv.ptr, ti.ptr, tp.ptr,
-                                                       kil.data_ptr(), C, xil.data_ptr(), C, None, 0))
+    out = {"workload": args.workload, "coils": C, "m": m, "k": k, "nnz": nnz}
+    # stored adjoint, tile-major rows
+    tile = (4, 4, 4)
+    grid3 = (ctypes.c_int64 * 3)(*oN); tile3 = (ctypes.c_int64 * 3)(*tile)
+    padded = ctypes.c_int64()
+    lib.grid_tile_rank(s, grid3, tile3, None, None, ctypes.byref(padded))
+    kp = padded.value
+    colrank = torch.empty(k, dtype=torch.int32, device="cuda")
+    rowmap = torch.empty(kp, dtype=torch.int32, device="cuda")
+    lib.grid_tile_rank(s, grid3, tile3, colrank.data_ptr(), rowmap.data_ptr(), ctypes.byref(padded))
+    t_ptr = torch.empty(kp + 1, dtype=torch.int32, device="cuda")
+    t_ind = torch.empty(nnz, dtype=torch.int32, device="cuda")
+    t_val = torch.empty(nnz * 2, dtype=torch.float32, device="cuda")
+    work = torch.empty(kp + 1, dtype=torch.int32, device="cuda")
+    t0 = time.time()
+    lib.csr_transpose_conj(s, m, kp, nnz, G.values.ptr, G.colInds.ptr, G.rowPtrs.ptr, t_val.data_ptr(),
+                           t_ind.data_ptr(), t_ptr.data_ptr(), work.data_ptr(), colrank.data_ptr())
+    torch.cuda.synchronize()
+    out["build_GH_s"] = round(time.time() - t0, 2)
+    lens = (t_ptr[1:] - t_ptr[:-1])
+    out["GH_row_len_max"] = int(lens.max().item())
+    out["GH_rows_gt_thresh"] = int((lens > args.thresh).sum().item())
+    out["GH_nnz_in_long_rows"] = int(lens[lens > args.thresh].sum().item())
+    cnt = ctypes.c_int()
+    lib.csr_long_rows(s, kp, t_ptr.data_ptr(), args.thresh, None, 0, ctypes.byref(cnt))
+    nlong = cnt.value
+    longrows = torch.empty(max(nlong, 1), dtype=torch.int32, device="cuda")
+    lib.csr_long_rows(s, kp, t_ptr.data_ptr(), args.thresh, longrows.data_ptr(), nlong, ctypes.byref(cnt))
+    hmax = (ctypes.c_float * 2)()
+    g_pk = torch.empty(nnz, dtype=torch.int64, device="cuda")
+    t_pk = torch.empty(nnz, dtype=torch.int64, device="cuda")
+    lib.csr_pack_real(s, nnz, G.values.ptr, G.colInds.ptr, g_pk.data_ptr(), hmax)
+    lib.csr_pack_real(s, nnz, t_val.data_ptr(), t_ind.data_ptr(), t_pk.data_ptr(), hmax)
+
+    fwd_c = lambda rpg: lib.ccsrmm_il(s, m, k, C, nnz, 1.0, 0.0, G.values.ptr, G.colInds.ptr, G.rowPtrs.ptr,
+                                      xil.data_ptr(), C, kil.data_ptr(), C, None, rpg, None, 0, 0)
+    fwd_r = lambda rpg: lib.ccsrmm_ilr(s, m, k, C, nnz, 1.0, 0.0, g_pk.data_ptr(), G.rowPtrs.ptr,
+                                       xil.data_ptr(), C, kil.data_ptr(), C, None, rpg, None, 0, 0)
+    adj_c = lambda nl: lib.ccsrmm_il(s, kp, m, C, nnz, 1.0, 0.0, t_val.data_ptr(), t_ind.data_ptr(), t_ptr.data_ptr(),
+                                     kil.data_ptr(), C, xil.data_ptr(), C, rowmap.data_ptr(), 1,
+                                     longrows.data_ptr(), nl, args.thresh)
+    adj_r = lambda nl: lib.ccsrmm_ilr(s, kp, m, C, nnz, 1.0, 0.0, t_pk.data_ptr(), t_ptr.data_ptr(),
+                                      kil.data_ptr(), C, xil.data_ptr(), C, rowmap.data_ptr(), 1,
+                                      longrows.data_ptr(), nl, args.thresh)
+    out["fwd_complex_ms"] = timed(lambda: fwd_c(0))
+    out["fwd_packed_ms"] = timed(lambda: fwd_r(0))
+    kil.normal_()
+    out["adj_complex_nosplit_ms"] = timed(lambda: adj_c(0))
     ref = xil.clone()
-    # stored adjoint with rows in tile-major order of the grid
-    for tile in ((4, 4, 4), (8, 4, 4), (8, 8, 8)):
-        grid3 = (ctypes.c_int64 * 3)(*oN); tile3 = (ctypes.c_int64 * 3)(*tile)
-        padded = ctypes.c_int64()
-        lib.grid_tile_rank(s, grid3, tile3, None, None, ctypes.byref(padded))
-        kp = padded.value
-        colrank = torch.empty(k, dtype=torch.int32, device="cuda")
-        rowmap = torch.empty(kp, dtype=torch.int32, device="cuda")
-        lib.grid_tile_rank(s, grid3, tile3, colrank.data_ptr(), rowmap.data_ptr(), ctypes.byref(padded))
-        t_ptr = torch.empty(kp + 1, dtype=torch.int32, device="cuda")
-        t_ind = torch.empty(nnz, dtype=torch.int32, device="cuda")
-        t_val = torch.empty(nnz * 2, dtype=torch.float32, device="cuda")
-        work = torch.empty(kp + 1, dtype=torch.int32, device="cuda")
-        t0 = time.time()
-        lib.csr_transpose_conj(s, m, kp, nnz, G.values.ptr, G.colInds.ptr, G.rowPtrs.ptr, t_val.data_ptr(),
-                               t_ind.data_ptr(), t_ptr.data_ptr(), work.data_ptr(), colrank.data_ptr())
-        torch.cuda.synchronize()
-        tag = "x".join(str(v) for v in tile)
-        out["build_GH_tiled_%s_s" % tag] = round(time.time() - t0, 2)
-        rows_per_tile = tile[0] * tile[1] * tile[2]
-        for rpg in sorted({max(1, rows_per_tile // 16), 1}):
-            xil.zero_()
-            out["adj_tiled_%s_rpg%d_ms" % (tag, rpg)] = timed(lambda: lib.ccsrmm_il(
-                s, kp, m, C, nnz, 1.0, 0.0, t_val.data_ptr(), t_ind.data_ptr(), t_ptr.data_ptr(), kil.data_ptr(), C,
-                xil.data_ptr(), C, rowmap.data_ptr(), rpg))
-            out["adj_tiled_%s_relerr" % tag] = float((xil - ref).norm() / ref.norm())
-        del colrank, rowmap, t_ptr, t_ind, t_val, work
-    out["interleave_grid_ms"] = timed(lambda: lib.interleave(s, k, C, xcm.data_ptr(), k, xil.data_ptr(), C))
-    out["deinterleave_grid_ms"] = timed(lambda: lib.deinterleave(s, k, C, xil.data_ptr(), C, 0.0, 0.0, xcm.data_ptr(), k))
+    out["adj_complex_split_ms"] = timed(lambda: adj_c(nlong))
+    out["adj_complex_split_relerr"] = float((xil - ref).norm() / ref.norm())
+    out["adj_packed_nosplit_ms"] = timed(lambda: adj_r(0))
+    out["adj_packed_split_ms"] = timed(lambda: adj_r(nlong))
+    out["adj_packed_split_relerr"] = float((xil - ref).norm() / ref.norm())
     alg = nnz * 12 + (m + 1) * 4 + 8 * C * (k + m)
-    out["alg_GB"] = alg / 1e9
-    out["fwd_gather_GBs"] = alg / out["fwd_gather_ms"] / 1e6
-    out["adj_gather_GBs"] = (alg + (k - m) * 4) / out["adj_gather_ms"] / 1e6
+    out["alg_GB"] = round(alg / 1e9, 3)
     print(json.dumps(out))
 
 

@@ -3,10 +3,10 @@
 TAG=${1:-g}
 NCU=${2:-0}
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_primitives.py -m gpu -x -q -k "csr" > gpurun_out/${TAG}_csr_tests.log 2>&1; tail -3 gpurun_out/${TAG}_csr_tests.log
+true
 timeout 900 python tools/bench_grid.py > gpurun_out/${TAG}_grid.json 2> gpurun_out/${TAG}_grid.err; cat gpurun_out/${TAG}_grid.json; tail -3 gpurun_out/${TAG}_grid.err
 if [ "$NCU" != "0" ]; then
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:csrmm_il -c 12 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:csrmm_il -c 20 \
     -o gpurun_out/${TAG}_il_full -f python tools/bench_grid.py --reps 0 > gpurun_out/${TAG}_ncu_il.log 2>&1
 tail -2 gpurun_out/${TAG}_ncu_il.log | cut -c1-300
 fi
