@@ -59,7 +59,9 @@ static int launch_spec_t(cudaStream_t s, const FftKernelArgs &k) {
 
 template <int N, int R0, int R1, int R2, bool AXIS0>
 static int launch_spec(cudaStream_t s, const FftKernelArgs &k) {
-    static const int threads = getenv("IB200_FFT_THREADS") ? atoi(getenv("IB200_FFT_THREADS")) : 256;
+    // 512 threads (two CTAs of 16 warps per SM) measured 15-20 % faster than 256 on the 416-point
+    // passes of cfg3 (profiles/r01_s4_*): the passes are issue/latency bound, not DRAM bound.
+    static const int threads = getenv("IB200_FFT_THREADS") ? atoi(getenv("IB200_FFT_THREADS")) : (N >= 128 ? 512 : 256);
     if (threads == 512) return launch_spec_t<N, R0, R1, R2, AXIS0, 512>(s, k);
     if (threads == 128) return launch_spec_t<N, R0, R1, R2, AXIS0, 128>(s, k);
     return launch_spec_t<N, R0, R1, R2, AXIS0, 256>(s, k);
@@ -80,15 +82,17 @@ static int try_spec(cudaStream_t s, bool axis0, const FftKernelArgs &k) {
 }
 
 // ---- fused SENSE x passes on the interleaved grid (fft_il.cuh) ---------------------------------
+static constexpr int sense_x_threads(int n) { return n >= 128 ? 512 : 256; }
+
 template <int N, int R0, int R1, int R2>
-__global__ void __launch_bounds__(256, 2) sense_expand_kernel(const SenseFftArgs a) {
+__global__ void __launch_bounds__(sense_x_threads(N), 2) sense_expand_kernel(const SenseFftArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     sense_expand_body<N, R0, R1, R2>(a, reinterpret_cast<c64 *>(smem_raw), (int64_t)blockIdx.x, (int)threadIdx.x,
                                      (int)blockDim.x);
 }
 
 template <int N, int R0, int R1, int R2>
-__global__ void __launch_bounds__(256, 2) sense_combine_kernel(const SenseFftArgs a) {
+__global__ void __launch_bounds__(sense_x_threads(N), 2) sense_combine_kernel(const SenseFftArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c64 *buf = reinterpret_cast<c64 *>(smem_raw);
     sense_combine_body<N, R0, R1, R2>(a, buf, buf + (size_t)2 * N * kSpecLP, (int64_t)blockIdx.x, (int)threadIdx.x,
@@ -109,8 +113,8 @@ static int launch_sense_x(cudaStream_t s, bool combine, const SenseFftArgs &a) {
     }
     const int64_t blocks = (int64_t)a.N1 * a.N2;
     IB200_REQUIRE(blocks < (1LL << 31), "sense x pass: too many rows for one launch");
-    if (combine) sense_combine_kernel<N, R0, R1, R2><<<(unsigned)blocks, 256, smem, s>>>(a);
-    else         sense_expand_kernel<N, R0, R1, R2><<<(unsigned)blocks, 256, smem, s>>>(a);
+    if (combine) sense_combine_kernel<N, R0, R1, R2><<<(unsigned)blocks, sense_x_threads(N), smem, s>>>(a);
+    else         sense_expand_kernel<N, R0, R1, R2><<<(unsigned)blocks, sense_x_threads(N), smem, s>>>(a);
     IB200_LAUNCH_CHECK();
     return 0;
 }
