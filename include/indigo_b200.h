@@ -133,6 +133,15 @@ int ib200_ccsrmm_ilr(void *stream, int64_t m, int64_t k, int64_t ncols, int64_t 
  * ib200_grid_tile_rank fills colrank[g] = padded tile-major rank of grid point g (x fastest)
  * and rowmap[rank] = g (or -1 for padding); *padded_rows = number of ranks.  Pass NULL for both
  * arrays to query the size only. */
+/* Stable re-ordering of the ROWS of a packed CSR matrix by the key colrank[first column of the row]
+ * (rows without entries go last): rowptr_out[m+1] / packed_out[nnz] hold the permuted matrix and
+ * rowmap_out[i] the original index of permuted row i, to be passed as `rowmap` to the products
+ * above.  With colrank from ib200_grid_tile_rank the samples of a trajectory end up grouped by
+ * the grid tile they fall into, so consecutive rows share operand lines in all three dimensions,
+ * not only along the readout.  nranks = number of distinct ranks (padded_rows).  Synchronises. */
+int ib200_csr_permute_rows(void *stream, int64_t m, int64_t nnz, const int32_t *rowptr, const void *packed,
+                           const int32_t *colrank, int64_t nranks, int32_t *rowptr_out, void *packed_out,
+                           int32_t *rowmap_out);
 /* Rows with more than long_thresh entries (the k-space centre of a radial trajectory puts ~80 000
  * entries into single rows of the stored adjoint) are listed once by ib200_csr_long_rows
  * (count returned through *host_count; call with capacity 0 to size the list; synchronises) and

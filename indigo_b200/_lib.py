@@ -38,6 +38,7 @@ SIGNATURES = {
     "ib200_deinterleave": (_i, [_vp, _i64, _i64, _vp, _i64, _f, _f, _vp, _i64]),
     "ib200_ccsrmm_il": (_i, [_vp, _i64, _i64, _i64, _i64, _f, _f, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i,
                              _vp, _i, _i]),
+    "ib200_csr_permute_rows": (_i, [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "ib200_csr_long_rows": (_i, [_vp, _i64, _vp, _i, _vp, _i, POINTER(_i)]),
     "ib200_csr_pack_real": (_i, [_vp, _i64, _vp, _vp, _vp, POINTER(c_float)]),
     "ib200_ccsrmm_ilr": (_i, [_vp, _i64, _i64, _i64, _i64, _f, _f, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i,

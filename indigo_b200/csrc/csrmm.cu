@@ -373,6 +373,41 @@ __global__ void __launch_bounds__(256) transpose_gather_kernel(int64_t nnz, cons
     }
 }
 
+// ---- row permutation of a packed CSR matrix (setup time) -------------------------------
+// Rows are re-ordered by an integer key (stable), e.g. the tile-major rank of a gridding row's
+// first grid point, so that the rows one CTA owns touch neighbouring operand lines in all
+// three dimensions instead of only along the readout.
+__global__ void __launch_bounds__(256) row_key_kernel(int64_t m, const int32_t *__restrict__ rowptr,
+                                                      const int2 *__restrict__ packed,
+                                                      const int32_t *__restrict__ colrank, int32_t nokey,
+                                                      int32_t *__restrict__ keys, int32_t *__restrict__ rows) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    const int p0 = rowptr[r], p1 = rowptr[r + 1];
+    keys[r] = p1 > p0 ? colrank[packed[p0].x] : nokey;
+    rows[r] = (int32_t)r;
+}
+
+__global__ void __launch_bounds__(256) perm_len_kernel(int64_t m, const int32_t *__restrict__ perm,
+                                                       const int32_t *__restrict__ rowptr, int32_t *__restrict__ lens) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int32_t r = perm[i];
+    lens[i] = rowptr[r + 1] - rowptr[r];
+}
+
+__global__ void __launch_bounds__(256) perm_copy_kernel(int64_t m, const int32_t *__restrict__ perm,
+                                                        const int32_t *__restrict__ rowptr,
+                                                        const int32_t *__restrict__ rowptr_out,
+                                                        const int2 *__restrict__ in, int2 *__restrict__ out) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int lane = threadIdx.x & 7;
+    if (i >= m) return;
+    const int32_t r = perm[i];
+    const int s0 = rowptr[r], n = rowptr[r + 1] - s0, d0 = rowptr_out[i];
+    for (int j = lane; j < n; j += 8) out[d0 + j] = in[s0 + j];
+}
+
 }  // namespace ib200
 
 using namespace ib200;
@@ -481,6 +516,50 @@ int ib200_csr_transpose_conj(void *stream, int64_t m, int64_t k, int64_t nnz, co
         e = cudaStreamSynchronize(s);
     }
     cudaFree(tmp); cudaFree(buf);
+    IB200_TRY(e);
+    IB200_TRY(cudaGetLastError());
+    return 0;
+}
+
+int ib200_csr_permute_rows(void *stream, int64_t m, int64_t nnz, const int32_t *rowptr, const void *packed,
+                           const int32_t *colrank, int64_t nranks, int32_t *rowptr_out, void *packed_out,
+                           int32_t *rowmap_out) {
+    IB200_REQUIRE(m >= 0 && nnz >= 0 && nnz < (1LL << 31) && nranks >= 0 && nranks < (1LL << 31) - 1, "bad dimensions");
+    IB200_REQUIRE(rowptr_out && rowmap_out, "null pointer");
+    cudaStream_t s = as_stream(stream);
+    if (m == 0) { IB200_TRY(cudaMemsetAsync(rowptr_out, 0, 4, s)); return 0; }
+    IB200_REQUIRE(rowptr && colrank && (nnz == 0 || (packed && packed_out)), "null pointer");
+    int32_t *buf = nullptr;
+    IB200_TRY(cudaMalloc(&buf, (size_t)m * sizeof(int32_t) * 4));
+    int32_t *keys_a = buf, *keys_b = buf + m, *rows_a = buf + 2 * m, *rows_b = buf + 3 * m;
+    row_key_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, s>>>(m, rowptr, (const int2 *)packed, colrank, (int32_t)nranks,
+                                                              keys_a, rows_a);
+    count_launch();
+    int end_bit = 1; while ((1LL << end_bit) <= nranks) ++end_bit;
+    cub::DoubleBuffer<int32_t> dk(keys_a, keys_b), dv(rows_a, rows_b);
+    size_t tmp_bytes = 0;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int)m, 0, end_bit, s);
+    void *tmp = nullptr;
+    if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16);
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, (int)m, 0, end_bit, s);
+    int rc = 0;
+    if (e == cudaSuccess) {
+        count_launch(end_bit / 8 + 2);
+        const int32_t *perm = dv.Current();
+        int32_t *lens = dk.Current();                              // keys are no longer needed
+        perm_len_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, s>>>(m, perm, rowptr, lens);
+        count_launch();
+        rc = exclusive_scan(s, m, lens, rowptr_out, rowptr_out + m);
+        if (!rc) {
+            perm_copy_kernel<<<(unsigned)ceil_div(m * 8, 256), 256, 0, s>>>(m, perm, rowptr, rowptr_out,
+                                                                            (const int2 *)packed, (int2 *)packed_out);
+            count_launch();
+            e = cudaMemcpyAsync(rowmap_out, perm, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToDevice, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        }
+    }
+    cudaFree(tmp); cudaFree(buf);
+    if (rc) return rc;
     IB200_TRY(e);
     IB200_TRY(cudaGetLastError());
     return 0;

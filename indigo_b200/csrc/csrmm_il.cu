@@ -357,6 +357,120 @@ static int launch_long(cudaStream_t s, int CL, int nlong, const int32_t *longrow
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// Staged variant of the real-weight gather (north star: "column indices staged through shared
+// memory").  A CTA owns R = GPB*RPG consecutive rows, i.e. one contiguous range of packed entries;
+// the range is streamed into shared memory with 16-byte cp.async copies (perfectly coalesced, no
+// register staging), after which an entry costs one LDS instead of a dependent global load: the
+// operand gathers of a row are then all independent and are issued U at a time.  Rows spanning
+// two chunks keep their partial sums in registers.  The packed array must be readable two
+// entries past its end (16-byte granules).
+static const int kStageChunk = 4096;                               // entries per chunk (32 KB)
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+template <int GL, int CL, int RPG, int U>
+__global__ void __launch_bounds__(256) csrmm_ils_kernel(int64_t m, int C, c64 alpha,
+                                                        const PackedEntry *__restrict__ ent,
+                                                        const int32_t *__restrict__ rowptr,
+                                                        const c64 *__restrict__ Xil, uint32_t xpitch_bytes,
+                                                        c64 *__restrict__ Yil, int64_t ypitch,
+                                                        const int32_t *__restrict__ rowmap, int long_thresh) {
+    constexpr int NP = GL / CL, GPB = 256 / GL, R = GPB * RPG;
+    constexpr unsigned FULL = 0xffffffffu;
+    __shared__ __align__(16) PackedEntry sent[kStageChunk + 2];
+    __shared__ int srp[R + 1];
+    const int gl = (int)(threadIdx.x & (GL - 1));
+    const int coil = gl & (CL - 1);
+    const int slot = gl / CL;
+    const int group = (int)(threadIdx.x / GL);
+    const char *xb = reinterpret_cast<const char *>(Xil + (coil < C ? coil : 0));
+    const int64_t r0 = (int64_t)blockIdx.x * R;
+    const int nr = m - r0 < R ? (int)(m - r0) : R;
+    for (int i = threadIdx.x; i <= nr; i += 256) srp[i] = __ldg(rowptr + r0 + i);
+    __syncthreads();
+    const int E0 = srp[0], E1 = srp[nr];
+    float ax[RPG], ay[RPG];
+#pragma unroll
+    for (int i = 0; i < RPG; ++i) { ax[i] = 0.f; ay[i] = 0.f; }
+    for (int c0 = E0 & ~1; c0 < E1; c0 += kStageChunk) {
+        const int cend = c0 + kStageChunk < E1 ? c0 + kStageChunk : E1;        // entries [c0, cend) are usable
+        for (int q = c0 + 2 * (int)threadIdx.x; q < cend; q += 512) cp_async16(sent + (q - c0), ent + q);
+        cp_async_wait_all();
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < RPG; ++i) {
+            const int row = group + i * GPB;
+            if (row < nr) {
+                int a = srp[row], b = srp[row + 1];
+                if (b - a > long_thresh) b = a;                                 // left to csrmm_il_long_kernel
+                a = a > c0 ? a : c0; b = b < cend ? b : cend;
+                const PackedEntry *se = sent - c0;
+                int p = a + slot;
+                float sx = 0.f, sy = 0.f, tx = 0.f, ty = 0.f;
+                for (; p + (U - 1) * NP < b; p += U * NP) {
+                    PackedEntry e[U];
+                    c64 x[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) e[u] = se[p + u * NP];
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        x[u] = __ldg(reinterpret_cast<const c64 *>(xb + (uint64_t)(uint32_t)e[u].col * xpitch_bytes));
+#pragma unroll
+                    for (int u = 0; u < U; u += 2) {
+                        sx = fmaf(e[u].w, x[u].x, sx); sy = fmaf(e[u].w, x[u].y, sy);
+                        tx = fmaf(e[u + 1].w, x[u + 1].x, tx); ty = fmaf(e[u + 1].w, x[u + 1].y, ty);
+                    }
+                }
+                for (; p < b; p += NP) {
+                    const PackedEntry e0 = se[p];
+                    const c64 x0 = __ldg(reinterpret_cast<const c64 *>(xb + (uint64_t)(uint32_t)e0.col * xpitch_bytes));
+                    sx = fmaf(e0.w, x0.x, sx); sy = fmaf(e0.w, x0.y, sy);
+                }
+                ax[i] += sx + tx; ay[i] += sy + ty;
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < RPG; ++i) {
+        c64 acc = mk(ax[i], ay[i]);
+        if (NP > 1) {
+#pragma unroll
+            for (int o = CL; o < GL; o <<= 1) {
+                acc.x += __shfl_xor_sync(FULL, acc.x, o, GL);
+                acc.y += __shfl_xor_sync(FULL, acc.y, o, GL);
+            }
+        }
+        const int row = group + i * GPB;
+        if (row < nr && slot == 0 && coil < C && srp[row + 1] - srp[row] <= long_thresh) {
+            const int64_t gr = r0 + row;
+            const int64_t out = rowmap ? (int64_t)__ldg(rowmap + gr) : gr;
+            if (out >= 0) __stcs(Yil + out * ypitch + coil, cmul(alpha, acc));
+        }
+    }
+}
+
+template <int GL, int CL, int RPG, int U>
+static int launch_ils(cudaStream_t s, int64_t m, int C, c64 alpha, const PackedEntry *ent, const int32_t *rowptr,
+                      const c64 *Xil, int64_t xpitch, c64 *Yil, int64_t ypitch, const int32_t *rowmap, int long_thresh) {
+    const int64_t rows_per_cta = (int64_t)(256 / GL) * RPG;
+    const int64_t blocks = ceil_div(m, rows_per_cta);
+    IB200_REQUIRE(blocks < (1LL << 31), "matrix too large for one launch");
+    IB200_REQUIRE(xpitch * (int64_t)sizeof(c64) < (1LL << 32), "operand pitch too large");
+    csrmm_ils_kernel<GL, CL, RPG, U><<<(unsigned)blocks, 256, 0, s>>>(m, C, alpha, ent, rowptr, Xil,
+                                                                      (uint32_t)(xpitch * sizeof(c64)), Yil, ypitch,
+                                                                      rowmap, long_thresh);
+    IB200_LAUNCH_CHECK();
+    return 0;
+}
+
 // packed[p] = (colind[p], Re vals[p]);  stats[0] = max |Re|, stats[1] = max |Im| (as float bit patterns, >= 0)
 __global__ void __launch_bounds__(256) pack_real_kernel(int64_t nnz, const c64 *__restrict__ vals,
                                                         const int32_t *__restrict__ colind,
@@ -580,6 +694,10 @@ int ib200_ccsrmm_ilr(void *stream, int64_t m, int64_t k, int64_t ncols, int64_t 
     if (nlong <= 0 || !longrows) { nlong = 0; long_thresh = 0x7fffffff; }
     IB200_REQUIRE(rowptr && Yil && (nnz == 0 || (packed && Xil)), "null pointer");
     IB200_REQUIRE(xpitch >= ncols && ypitch >= ncols, "pitch smaller than the column count");
+    // rows_per_group < 0 selects the shared-memory staged kernel (-4: four operand loads in flight per
+    // lane, -8: eight); the packed array must then be readable two entries past its end
+    const int staged = rows_per_group < 0 ? -rows_per_group : 0;
+    if (staged) rows_per_group = 0;
     IB200_REQUIRE(rows_per_group >= 0 && rows_per_group <= 4096, "rows_per_group out of range");
     const int CL = pow2_ceil(ncols);
     const double avg = (double)nnz / (double)m;
@@ -593,6 +711,19 @@ int ib200_ccsrmm_ilr(void *stream, int64_t m, int64_t k, int64_t ncols, int64_t 
     int rc = launch_long<true>(s, CL, nlong, longrows, (int)ncols, alpha, packed, nullptr, nullptr, rowptr,
                                (const c64 *)Xil, xpitch, (c64 *)Yil, ypitch, rowmap);
     if (rc) return rc;
+    if (staged) {                                                  // shared-memory staged entries, 4 rows per group
+        const int U = staged >= 8 ? 8 : 4;
+#define IB200_ILS_CASE(gl, cl) \
+    case (gl) * 100 + (cl): return U == 8 \
+        ? launch_ils<gl, cl, 4, 8>(s, m, (int)ncols, alpha, (const PackedEntry *)packed, rowptr, (const c64 *)Xil, xpitch, (c64 *)Yil, ypitch, rowmap, long_thresh) \
+        : launch_ils<gl, cl, 4, 4>(s, m, (int)ncols, alpha, (const PackedEntry *)packed, rowptr, (const c64 *)Xil, xpitch, (c64 *)Yil, ypitch, rowmap, long_thresh)
+        switch (GL * 100 + CL) {
+            IB200_ILS_CASE(2, 2); IB200_ILS_CASE(4, 2); IB200_ILS_CASE(4, 4); IB200_ILS_CASE(8, 2); IB200_ILS_CASE(8, 4);
+            IB200_ILS_CASE(8, 8); IB200_ILS_CASE(16, 2); IB200_ILS_CASE(16, 4); IB200_ILS_CASE(16, 8); IB200_ILS_CASE(16, 16);
+            IB200_ILS_CASE(32, 2); IB200_ILS_CASE(32, 4); IB200_ILS_CASE(32, 8); IB200_ILS_CASE(32, 16); IB200_ILS_CASE(32, 32);
+        }
+#undef IB200_ILS_CASE
+    }
 #define IB200_ILR_CASE(gl, cl) \
     case (gl) * 100 + (cl): return launch_ilr<gl, cl>(s, m, (int)ncols, alpha, (const PackedEntry *)packed, rowptr, (const c64 *)Xil, xpitch, (c64 *)Yil, ypitch, rowmap, rpg, long_thresh)
     switch (GL * 100 + CL) {

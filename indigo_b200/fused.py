@@ -32,6 +32,8 @@ class SenseDevice(object):
     tile = (4, 4, 4)
     allow_real = True          # use the real-weight packed kernels when the matrix values are real
     long_thresh = 512          # rows of G'^H with more entries than this get a whole CTA each
+    sample_tile = (8, 8, 8)    # samples (rows of G') are sorted by the grid tile of this size they fall into
+    staged = -4                # rows_per_group code of ib200_ccsrmm_ilr: shared-memory staged entries, 4 loads in flight
 
     def __init__(self, B, N, coord, maps, oversamp=2.0, weights=None, width=3, n=128):
         from .sense import gridding_matrix_device, _fftc_mod
@@ -78,14 +80,29 @@ class SenseDevice(object):
         self.real = False
         if self.nnz and self.allow_real:
             pk = np.dtype('int64')                                     # 8-byte (int32 column, float32 weight) records
-            g_pk = B.empty_array((self.nnz,), pk, name='G.packed')
+            g_pk = B.zero_array((self.nnz + 2,), pk, name='G.packed')  # +2: the staged kernel copies 16-byte granules
             hmax = (ctypes.c_float * 2)()
             lib.csr_pack_real(s, self.nnz, self.G.values.ptr, self.G.colInds.ptr, g_pk.ptr, hmax)
             if hmax[1] <= 1e-8 * hmax[0]:
-                t_pk = B.empty_array((self.nnz,), pk, name='G.H.packed')
+                t_pk = B.zero_array((self.nnz + 2,), pk, name='G.H.packed')
                 lib.csr_pack_real(s, self.nnz, self.t_val.ptr, self.t_ind.ptr, t_pk.ptr, hmax)
-                self.g_pk, self.t_pk, self.real = g_pk, t_pk, True
+                self.t_pk, self.real = t_pk, True
                 self.t_val = self.t_ind = None                          # the complex copy of G'^H is not needed any more
+                # samples sorted by the 8x8x8 grid tile they fall into: the rows one CTA owns then share
+                # operand lines in all three dimensions (L1) and neighbouring CTAs share them in L2
+                stile = (ctypes.c_int64 * 3)(*self.sample_tile)
+                lib.grid_tile_rank(s, grid3, stile, None, None, ctypes.byref(padded))
+                nr8 = int(padded.value)
+                rank8 = B.empty_array((self.on,), i32)
+                junk = B.empty_array((nr8,), i32)
+                lib.grid_tile_rank(s, grid3, stile, rank8.ptr, junk.ptr, ctypes.byref(padded))
+                self.g_ptr = B.empty_array((self.M + 1,), i32, name='G.sorted.rowPtrs')
+                self.g_pk = B.zero_array((self.nnz + 2,), pk, name='G.sorted.packed')
+                self.g_map = B.empty_array((max(self.M, 1),), i32, name='G.sorted.rowmap')
+                lib.csr_permute_rows(s, self.M, self.nnz, self.G.rowPtrs.ptr, g_pk.ptr, rank8.ptr, nr8,
+                                     self.g_ptr.ptr, self.g_pk.ptr, self.g_map.ptr)
+                del rank8, junk
+            del g_pk
         # rows of G'^H that are long enough to deserve a whole CTA (k-space centre of radial trajectories)
         cnt = ctypes.c_int()
         lib.csr_long_rows(s, kp, self.t_ptr.ptr, self.long_thresh, None, 0, ctypes.byref(cnt))
@@ -113,8 +130,8 @@ class SenseDevice(object):
         a = complex(alpha)
         G, lib, s = self.G, self.B._lib, self.B._stream
         if self.real:
-            lib.ccsrmm_ilr(s, self.M, self.on, self.C, self.nnz, a.real, a.imag, self.g_pk.ptr, G.rowPtrs.ptr,
-                           self.grid.ptr, self.C, self.ksp.ptr, self.C, None, 0, None, 0, 0)
+            lib.ccsrmm_ilr(s, self.M, self.on, self.C, self.nnz, a.real, a.imag, self.g_pk.ptr, self.g_ptr.ptr,
+                           self.grid.ptr, self.C, self.ksp.ptr, self.C, self.g_map.ptr, self.staged, None, 0, 0)
         else:
             lib.ccsrmm_il(s, self.M, self.on, self.C, self.nnz, a.real, a.imag, G.values.ptr, G.colInds.ptr,
                           G.rowPtrs.ptr, self.grid.ptr, self.C, self.ksp.ptr, self.C, None, 0, None, 0, 0)
@@ -124,7 +141,8 @@ class SenseDevice(object):
         lr = self.longrows.ptr if self.nlong else None
         if self.real:
             lib.ccsrmm_ilr(s, self.kp, self.M, self.C, self.nnz, 1.0, 0.0, self.t_pk.ptr, self.t_ptr.ptr,
-                           self.ksp.ptr, self.C, self.grid.ptr, self.C, self.rowmap.ptr, 1, lr, self.nlong, self.long_thresh)
+                           self.ksp.ptr, self.C, self.grid.ptr, self.C, self.rowmap.ptr, self.staged, lr, self.nlong,
+                           self.long_thresh)
         else:
             lib.ccsrmm_il(s, self.kp, self.M, self.C, self.nnz, 1.0, 0.0, self.t_val.ptr, self.t_ind.ptr,
                           self.t_ptr.ptr, self.ksp.ptr, self.C, self.grid.ptr, self.C, self.rowmap.ptr, 1,

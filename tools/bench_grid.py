@@ -82,8 +82,8 @@ def main():
     longrows = torch.empty(max(nlong, 1), dtype=torch.int32, device="cuda")
     lib.csr_long_rows(s, kp, t_ptr.data_ptr(), args.thresh, longrows.data_ptr(), nlong, ctypes.byref(cnt))
     hmax = (ctypes.c_float * 2)()
-    g_pk = torch.empty(nnz, dtype=torch.int64, device="cuda")
-    t_pk = torch.empty(nnz, dtype=torch.int64, device="cuda")
+    g_pk = torch.zeros(nnz + 2, dtype=torch.int64, device="cuda")
+    t_pk = torch.zeros(nnz + 2, dtype=torch.int64, device="cuda")
     lib.csr_pack_real(s, nnz, G.values.ptr, G.colInds.ptr, g_pk.data_ptr(), hmax)
     lib.csr_pack_real(s, nnz, t_val.data_ptr(), t_ind.data_ptr(), t_pk.data_ptr(), hmax)
 
@@ -107,6 +107,50 @@ def main():
     out["adj_packed_nosplit_ms"] = timed(lambda: adj_r(0))
     out["adj_packed_split_ms"] = timed(lambda: adj_r(nlong))
     out["adj_packed_split_relerr"] = float((xil - ref).norm() / ref.norm())
+    # shared-memory staged variants (rows_per_group = -4 / -8)
+    kref = torch.empty_like(kil); xsave = xil.clone()
+    xil.normal_()
+    lib.ccsrmm_ilr(s, m, k, C, nnz, 1.0, 0.0, g_pk.data_ptr(), G.rowPtrs.ptr, xil.data_ptr(), C, kref.data_ptr(), C, None, 0, None, 0, 0)
+    for u in (4, 8):
+        out["fwd_staged_u%d_ms" % u] = timed(lambda: lib.ccsrmm_ilr(
+            s, m, k, C, nnz, 1.0, 0.0, g_pk.data_ptr(), G.rowPtrs.ptr, xil.data_ptr(), C, kil.data_ptr(), C, None, -u, None, 0, 0))
+        out["fwd_staged_u%d_relerr" % u] = float((kil - kref).norm() / kref.norm())
+    kil.normal_()
+    xref = torch.empty_like(xil)
+    lib.ccsrmm_ilr(s, kp, m, C, nnz, 1.0, 0.0, t_pk.data_ptr(), t_ptr.data_ptr(), kil.data_ptr(), C, xref.data_ptr(), C,
+                   rowmap.data_ptr(), 1, longrows.data_ptr(), nlong, args.thresh)
+    for u in (4, 8):
+        xil.zero_()
+        out["adj_staged_u%d_ms" % u] = timed(lambda: lib.ccsrmm_ilr(
+            s, kp, m, C, nnz, 1.0, 0.0, t_pk.data_ptr(), t_ptr.data_ptr(), kil.data_ptr(), C, xil.data_ptr(), C,
+            rowmap.data_ptr(), -u, longrows.data_ptr(), nlong, args.thresh))
+        out["adj_staged_u%d_relerr" % u] = float((xil - xref).norm() / xref.norm())
+    # forward with the samples sorted by grid tile (rows permuted at setup, outputs scattered through rowmap)
+    xil.normal_()
+    lib.ccsrmm_ilr(s, m, k, C, nnz, 1.0, 0.0, g_pk.data_ptr(), G.rowPtrs.ptr, xil.data_ptr(), C, kref.data_ptr(), C, None, 0, None, 0, 0)
+    for stile in ((8, 8, 8), (16, 8, 8), (16, 16, 16)):
+        st3 = (ctypes.c_int64 * 3)(*stile)
+        lib.grid_tile_rank(s, grid3, st3, None, None, ctypes.byref(padded))
+        kp2 = padded.value
+        cr2 = torch.empty(k, dtype=torch.int32, device="cuda"); rm2 = torch.empty(kp2, dtype=torch.int32, device="cuda")
+        lib.grid_tile_rank(s, grid3, st3, cr2.data_ptr(), rm2.data_ptr(), ctypes.byref(padded))
+        del rm2
+        g_ptr2 = torch.empty(m + 1, dtype=torch.int32, device="cuda")
+        g_pk2 = torch.zeros(nnz + 2, dtype=torch.int64, device="cuda")
+        g_map = torch.empty(m, dtype=torch.int32, device="cuda")
+        t0 = time.time()
+        lib.csr_permute_rows(s, m, nnz, G.rowPtrs.ptr, g_pk.data_ptr(), cr2.data_ptr(), kp2, g_ptr2.data_ptr(),
+                             g_pk2.data_ptr(), g_map.data_ptr())
+        torch.cuda.synchronize()
+        tag = "x".join(str(v) for v in stile)
+        out["sort_rows_%s_s" % tag] = round(time.time() - t0, 3)
+        for mode in (0, -4):
+            kil.zero_()
+            out["fwd_sorted_%s_%s_ms" % (tag, "staged" if mode else "plain")] = timed(lambda: lib.ccsrmm_ilr(
+                s, m, k, C, nnz, 1.0, 0.0, g_pk2.data_ptr(), g_ptr2.data_ptr(), xil.data_ptr(), C, kil.data_ptr(), C,
+                g_map.data_ptr(), mode, None, 0, 0))
+            out["fwd_sorted_%s_relerr" % tag] = float((kil - kref).norm() / kref.norm())
+        del cr2, g_ptr2, g_pk2, g_map
     alg = nnz * 12 + (m + 1) * 4 + 8 * C * (k + m)
     out["alg_GB"] = round(alg / 1e9, 3)
     print(json.dumps(out))
