@@ -375,7 +375,21 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
-template <int GL, int CL, int RPG, int U>
+// VC = coils per lane (1: 8-byte operand loads, 2: 16-byte loads of two neighbouring coils, which
+// halves the instructions per entry and doubles the rows a warp serves; needs an even coil count).
+template <int VC> struct CoilVec;
+template <> struct CoilVec<1> {
+    float x[1], y[1];
+    __device__ __forceinline__ void load(const char *p) { const c64 v = __ldg(reinterpret_cast<const c64 *>(p)); x[0] = v.x; y[0] = v.y; }
+};
+template <> struct CoilVec<2> {
+    float x[2], y[2];
+    __device__ __forceinline__ void load(const char *p) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(p)); x[0] = v.x; y[0] = v.y; x[1] = v.z; y[1] = v.w;
+    }
+};
+
+template <int GL, int CL, int RPG, int U, int VC>
 __global__ void __launch_bounds__(256) csrmm_ils_kernel(int64_t m, int C, c64 alpha,
                                                         const PackedEntry *__restrict__ ent,
                                                         const int32_t *__restrict__ rowptr,
@@ -387,7 +401,7 @@ __global__ void __launch_bounds__(256) csrmm_ils_kernel(int64_t m, int C, c64 al
     __shared__ __align__(16) PackedEntry sent[kStageChunk + 2];
     __shared__ int srp[R + 1];
     const int gl = (int)(threadIdx.x & (GL - 1));
-    const int coil = gl & (CL - 1);
+    const int coil = (gl & (CL - 1)) * VC;                          // first coil of this lane
     const int slot = gl / CL;
     const int group = (int)(threadIdx.x / GL);
     const char *xb = reinterpret_cast<const char *>(Xil + (coil < C ? coil : 0));
@@ -396,9 +410,20 @@ __global__ void __launch_bounds__(256) csrmm_ils_kernel(int64_t m, int C, c64 al
     for (int i = threadIdx.x; i <= nr; i += 256) srp[i] = __ldg(rowptr + r0 + i);
     __syncthreads();
     const int E0 = srp[0], E1 = srp[nr];
-    float ax[RPG], ay[RPG];
+    if (E0 == E1) {                                                 // no entries at all (grid tiles outside the sampled region)
+        for (int i = threadIdx.x; i < nr * C; i += 256) {
+            const int row = i / C, cc = i - row * C;
+            const int64_t gr = r0 + row;
+            const int64_t out = rowmap ? (int64_t)__ldg(rowmap + gr) : gr;
+            if (out >= 0) __stcs(Yil + out * ypitch + cc, mk(0.f, 0.f));
+        }
+        return;
+    }
+    float ax[RPG][VC], ay[RPG][VC];
 #pragma unroll
-    for (int i = 0; i < RPG; ++i) { ax[i] = 0.f; ay[i] = 0.f; }
+    for (int i = 0; i < RPG; ++i)
+#pragma unroll
+        for (int v = 0; v < VC; ++v) { ax[i][v] = 0.f; ay[i][v] = 0.f; }
     for (int c0 = E0 & ~1; c0 < E1; c0 += kStageChunk) {
         const int cend = c0 + kStageChunk < E1 ? c0 + kStageChunk : E1;        // entries [c0, cend) are usable
         for (int q = c0 + 2 * (int)threadIdx.x; q < cend; q += 512) cp_async16(sent + (q - c0), ent + q);
@@ -413,60 +438,72 @@ __global__ void __launch_bounds__(256) csrmm_ils_kernel(int64_t m, int C, c64 al
                 a = a > c0 ? a : c0; b = b < cend ? b : cend;
                 const PackedEntry *se = sent - c0;
                 int p = a + slot;
-                float sx = 0.f, sy = 0.f, tx = 0.f, ty = 0.f;
                 for (; p + (U - 1) * NP < b; p += U * NP) {
                     PackedEntry e[U];
-                    c64 x[U];
+                    CoilVec<VC> x[U];
 #pragma unroll
                     for (int u = 0; u < U; ++u) e[u] = se[p + u * NP];
 #pragma unroll
-                    for (int u = 0; u < U; ++u)
-                        x[u] = __ldg(reinterpret_cast<const c64 *>(xb + (uint64_t)(uint32_t)e[u].col * xpitch_bytes));
+                    for (int u = 0; u < U; ++u) x[u].load(xb + (uint64_t)(uint32_t)e[u].col * xpitch_bytes);
 #pragma unroll
-                    for (int u = 0; u < U; u += 2) {
-                        sx = fmaf(e[u].w, x[u].x, sx); sy = fmaf(e[u].w, x[u].y, sy);
-                        tx = fmaf(e[u + 1].w, x[u + 1].x, tx); ty = fmaf(e[u + 1].w, x[u + 1].y, ty);
-                    }
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int v = 0; v < VC; ++v) {
+                            ax[i][v] = fmaf(e[u].w, x[u].x[v], ax[i][v]); ay[i][v] = fmaf(e[u].w, x[u].y[v], ay[i][v]);
+                        }
                 }
                 for (; p < b; p += NP) {
                     const PackedEntry e0 = se[p];
-                    const c64 x0 = __ldg(reinterpret_cast<const c64 *>(xb + (uint64_t)(uint32_t)e0.col * xpitch_bytes));
-                    sx = fmaf(e0.w, x0.x, sx); sy = fmaf(e0.w, x0.y, sy);
+                    CoilVec<VC> x0;
+                    x0.load(xb + (uint64_t)(uint32_t)e0.col * xpitch_bytes);
+#pragma unroll
+                    for (int v = 0; v < VC; ++v) { ax[i][v] = fmaf(e0.w, x0.x[v], ax[i][v]); ay[i][v] = fmaf(e0.w, x0.y[v], ay[i][v]); }
                 }
-                ax[i] += sx + tx; ay[i] += sy + ty;
             }
         }
         __syncthreads();
     }
 #pragma unroll
     for (int i = 0; i < RPG; ++i) {
-        c64 acc = mk(ax[i], ay[i]);
-        if (NP > 1) {
+        const int row = group + i * GPB;
+        c64 acc[VC];
 #pragma unroll
-            for (int o = CL; o < GL; o <<= 1) {
-                acc.x += __shfl_xor_sync(FULL, acc.x, o, GL);
-                acc.y += __shfl_xor_sync(FULL, acc.y, o, GL);
+        for (int v = 0; v < VC; ++v) {
+            acc[v] = mk(ax[i][v], ay[i][v]);
+            if (NP > 1) {
+#pragma unroll
+                for (int o = CL; o < GL; o <<= 1) {
+                    acc[v].x += __shfl_xor_sync(FULL, acc[v].x, o, GL);
+                    acc[v].y += __shfl_xor_sync(FULL, acc[v].y, o, GL);
+                }
             }
         }
-        const int row = group + i * GPB;
         if (row < nr && slot == 0 && coil < C && srp[row + 1] - srp[row] <= long_thresh) {
             const int64_t gr = r0 + row;
             const int64_t out = rowmap ? (int64_t)__ldg(rowmap + gr) : gr;
-            if (out >= 0) __stcs(Yil + out * ypitch + coil, cmul(alpha, acc));
+            if (out >= 0) {
+                c64 *yp = Yil + out * ypitch + coil;
+                if (VC == 2) {
+                    const c64 o0 = cmul(alpha, acc[0]), o1 = cmul(alpha, acc[VC - 1]);
+                    __stcs(reinterpret_cast<float4 *>(yp), make_float4(o0.x, o0.y, o1.x, o1.y));
+                } else {
+                    __stcs(yp, cmul(alpha, acc[0]));
+                }
+            }
         }
     }
 }
 
-template <int GL, int CL, int RPG, int U>
+template <int GL, int CL, int RPG, int U, int VC>
 static int launch_ils(cudaStream_t s, int64_t m, int C, c64 alpha, const PackedEntry *ent, const int32_t *rowptr,
                       const c64 *Xil, int64_t xpitch, c64 *Yil, int64_t ypitch, const int32_t *rowmap, int long_thresh) {
     const int64_t rows_per_cta = (int64_t)(256 / GL) * RPG;
     const int64_t blocks = ceil_div(m, rows_per_cta);
     IB200_REQUIRE(blocks < (1LL << 31), "matrix too large for one launch");
     IB200_REQUIRE(xpitch * (int64_t)sizeof(c64) < (1LL << 32), "operand pitch too large");
-    csrmm_ils_kernel<GL, CL, RPG, U><<<(unsigned)blocks, 256, 0, s>>>(m, C, alpha, ent, rowptr, Xil,
-                                                                      (uint32_t)(xpitch * sizeof(c64)), Yil, ypitch,
-                                                                      rowmap, long_thresh);
+    csrmm_ils_kernel<GL, CL, RPG, U, VC><<<(unsigned)blocks, 256, 0, s>>>(m, C, alpha, ent, rowptr, Xil,
+                                                                          (uint32_t)(xpitch * sizeof(c64)), Yil, ypitch,
+                                                                          rowmap, long_thresh);
     IB200_LAUNCH_CHECK();
     return 0;
 }
@@ -694,8 +731,8 @@ int ib200_ccsrmm_ilr(void *stream, int64_t m, int64_t k, int64_t ncols, int64_t 
     if (nlong <= 0 || !longrows) { nlong = 0; long_thresh = 0x7fffffff; }
     IB200_REQUIRE(rowptr && Yil && (nnz == 0 || (packed && Xil)), "null pointer");
     IB200_REQUIRE(xpitch >= ncols && ypitch >= ncols, "pitch smaller than the column count");
-    // rows_per_group < 0 selects the shared-memory staged kernel (-4: four operand loads in flight per
-    // lane, -8: eight); the packed array must then be readable two entries past its end
+    // rows_per_group < 0 selects the shared-memory staged kernel (-4; -41 forces one coil per lane);
+    // the packed array must then be readable two entries past its end
     const int staged = rows_per_group < 0 ? -rows_per_group : 0;
     if (staged) rows_per_group = 0;
     IB200_REQUIRE(rows_per_group >= 0 && rows_per_group <= 4096, "rows_per_group out of range");
@@ -712,12 +749,18 @@ int ib200_ccsrmm_ilr(void *stream, int64_t m, int64_t k, int64_t ncols, int64_t 
                                (const c64 *)Xil, xpitch, (c64 *)Yil, ypitch, rowmap);
     if (rc) return rc;
     if (staged) {                                                  // shared-memory staged entries, 4 rows per group
-        const int U = staged >= 8 ? 8 : 4;
+        // two coils per lane (16-byte operand loads) whenever the layout allows it
+        const bool vec2 = staged != 41 && ncols % 2 == 0 && xpitch % 2 == 0 && ypitch % 2 == 0 &&
+                          ((uintptr_t)Xil % 16) == 0 && ((uintptr_t)Yil % 16) == 0;
+        const int CLv = vec2 ? pow2_ceil(ncols / 2) : CL;
+        int GLv = CLv;
+        while (GLv < 32 && avg >= 4.0 * GLv) GLv <<= 1;
 #define IB200_ILS_CASE(gl, cl) \
-    case (gl) * 100 + (cl): return U == 8 \
-        ? launch_ils<gl, cl, 4, 8>(s, m, (int)ncols, alpha, (const PackedEntry *)packed, rowptr, (const c64 *)Xil, xpitch, (c64 *)Yil, ypitch, rowmap, long_thresh) \
-        : launch_ils<gl, cl, 4, 4>(s, m, (int)ncols, alpha, (const PackedEntry *)packed, rowptr, (const c64 *)Xil, xpitch, (c64 *)Yil, ypitch, rowmap, long_thresh)
-        switch (GL * 100 + CL) {
+    case (gl) * 100 + (cl): return vec2 \
+        ? launch_ils<gl, cl, 4, 4, 2>(s, m, (int)ncols, alpha, (const PackedEntry *)packed, rowptr, (const c64 *)Xil, xpitch, (c64 *)Yil, ypitch, rowmap, long_thresh) \
+        : launch_ils<gl, cl, 4, 4, 1>(s, m, (int)ncols, alpha, (const PackedEntry *)packed, rowptr, (const c64 *)Xil, xpitch, (c64 *)Yil, ypitch, rowmap, long_thresh)
+        switch (GLv * 100 + CLv) {
+            IB200_ILS_CASE(1, 1); IB200_ILS_CASE(2, 1); IB200_ILS_CASE(4, 1); IB200_ILS_CASE(8, 1); IB200_ILS_CASE(16, 1); IB200_ILS_CASE(32, 1);
             IB200_ILS_CASE(2, 2); IB200_ILS_CASE(4, 2); IB200_ILS_CASE(4, 4); IB200_ILS_CASE(8, 2); IB200_ILS_CASE(8, 4);
             IB200_ILS_CASE(8, 8); IB200_ILS_CASE(16, 2); IB200_ILS_CASE(16, 4); IB200_ILS_CASE(16, 8); IB200_ILS_CASE(16, 16);
             IB200_ILS_CASE(32, 2); IB200_ILS_CASE(32, 4); IB200_ILS_CASE(32, 8); IB200_ILS_CASE(32, 16); IB200_ILS_CASE(32, 32);

@@ -119,6 +119,47 @@ static int launch_sense_x(cudaStream_t s, bool combine, const SenseFftArgs &a) {
     return 0;
 }
 
+template <int N, int R0, int R1, int R2, bool SI, bool SO>
+__global__ void __launch_bounds__(sense_x_threads(N), 2) fft_il_pass_kernel(const IlPassArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    fft_il_pass_body<N, R0, R1, R2, SI, SO>(a, reinterpret_cast<c64 *>(smem_raw), (int64_t)blockIdx.x, (int)threadIdx.x,
+                                            (int)blockDim.x);
+}
+
+template <int N, int R0, int R1, int R2, bool SI, bool SO>
+static int launch_il_pass(cudaStream_t s, const IlPassArgs &a) {
+    static bool attr_done[64] = {false};
+    const size_t smem = (size_t)(R2 > 1 ? 2 : 1) * N * kSpecLP * sizeof(c64);
+    int dev = 0;
+    IB200_TRY(cudaGetDevice(&dev));
+    if (!attr_done[dev & 63]) {
+        IB200_TRY(cudaFuncSetAttribute(fft_il_pass_kernel<N, R0, R1, R2, SI, SO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[dev & 63] = true;
+    }
+    const int64_t blocks = (a.inner / kSpecL) * a.outer;
+    IB200_REQUIRE(blocks < (1LL << 31), "fft: too many tiles for one launch");
+    fft_il_pass_kernel<N, R0, R1, R2, SI, SO><<<(unsigned)blocks, sense_x_threads(N), smem, s>>>(a);
+    IB200_LAUNCH_CHECK();
+    return 0;
+}
+
+// returns 1 when launched, 0 when no specialised size matches, else an error code (+1000 when positive)
+static int try_il_pass(cudaStream_t s, const IlPassArgs &a, int n, const FftStages &st, bool swap_in, bool swap_out) {
+    FftKernelArgs k;
+    k.n = n; k.st = st;
+#define IB200_IL_PASS(nn, r0, r1, r2)                                                            \
+    if (fft_spec_matches(k, nn, r0, r1, r2)) {                                                   \
+        int rc;                                                                                  \
+        if (swap_in)       rc = launch_il_pass<nn, r0, r1, r2, true, false>(s, a);               \
+        else if (swap_out) rc = launch_il_pass<nn, r0, r1, r2, false, true>(s, a);               \
+        else               rc = launch_il_pass<nn, r0, r1, r2, false, false>(s, a);              \
+        return rc == 0 ? 1 : (rc > 0 ? rc + 1000 : rc);                                          \
+    }
+    IB200_FFT_SPEC_LIST(IB200_IL_PASS)
+#undef IB200_IL_PASS
+    return 0;
+}
+
 static int run_sense_x(cudaStream_t s, bool combine, const SenseFftArgs &a, const FftStages &st) {
     FftKernelArgs k;
     k.n = a.n0; k.st = st;
@@ -262,6 +303,14 @@ static int sense_strided_pass(ib200_sense_plan_s *p, cudaStream_t s, c64 *grid, 
         k.inner = sz; k.outer = 1; k.outer_stride = sz * p->oN[2];
     }
     k.x = base; k.y = base;
+    if (k.inner % kSpecL == 0 && k.inner < (1LL << 32) && !(k.swap_in && k.swap_out) && getenv("IB200_FFT_IL_GENERIC") == nullptr) {
+        IlPassArgs a;
+        a.x = base; a.tw = ax.tw_dev; a.inner = k.inner; a.outer = k.outer; a.outer_stride = k.outer_stride;
+        a.pstride = (unsigned)k.inner; a.in0 = k.in0; a.in1 = k.in1; a.out0 = k.out0; a.out1 = k.out1;
+        const int r = try_il_pass(s, a, ax.n, ax.st, k.swap_in != 0, k.swap_out != 0);
+        if (r == 1) return 0;
+        if (r != 0) return r > 1000 ? r - 1000 : r;
+    }
     const int rc = try_spec(s, false, k);
     if (rc == 1) return 0;
     if (rc == 0) { set_error("fused SENSE passes need a grid extent with a specialised FFT (axis %d: %d)", axis, ax.n); return IB200_E_UNSUPPORTED; }

@@ -378,6 +378,33 @@ IB_HD void fft_pass_body(const FftKernelArgs &a, c64 *bufA, int64_t block, int t
 // ============================================================================
 static const int kSpecL = 16, kSpecLP = 17;
 
+// Lean tile context of the fused interleaved passes (fft_il.cuh): always 16 full lines of stride 1,
+// no diagonals, re/im swaps fixed at compile time, windows as one unsigned compare, 32-bit position
+// stride (one IMAD.WIDE per access instead of the generic 64-bit index arithmetic of FftCtx).
+template <bool SWAP_IN, bool SWAP_OUT>
+struct IlCtx {
+    const c64 *gin;
+    c64 *gout;
+    const c64 *tw;
+    unsigned pstride;                  // elements between consecutive positions of a line
+    int in0; unsigned inlen;           // input window  [in0, in0 + inlen)
+    int out0; unsigned outlen;         // output window [out0, out0 + outlen)
+    static constexpr int nl = kSpecL;
+};
+
+template <bool SI, bool SO>
+IB_HD c64 fft_gload(const IlCtx<SI, SO> &c, int l, int j) {
+    if ((unsigned)(j - c.in0) >= c.inlen) return h_mk(0.f, 0.f);
+    const c64 v = c.gin[(uint64_t)(unsigned)j * c.pstride + (unsigned)l];
+    return SI ? h_swap(v) : v;
+}
+
+template <bool SI, bool SO>
+IB_HD void fft_gstore(const IlCtx<SI, SO> &c, int l, int j, c64 v) {
+    if ((unsigned)(j - c.out0) >= c.outlen) return;
+    c.gout[(uint64_t)(unsigned)j * c.pstride + (unsigned)l] = SO ? h_swap(v) : v;
+}
+
 // powers w^1 .. w^(R-1) with multiplication depth log2(R)
 template <int R>
 IB_HD void twiddle_powers(c64 w, c64 (&pw)[R]) {
@@ -396,8 +423,8 @@ IB_HD int spec_addr(int pos, int l) {
 }
 
 // lines-fast stage (strided axes: every stage; axis 0: the middle stage)
-template <int N, int R, int P, bool SRC_G, bool DST_G, int ROT_IN, int ROT_OUT>
-IB_HD void spec_stage_lfast(const FftCtx &c, const c64 *sin_, c64 *sout, int tid, int nt) {
+template <int N, int R, int P, bool SRC_G, bool DST_G, int ROT_IN, int ROT_OUT, class CTX>
+IB_HD void spec_stage_lfast(const CTX &c, const c64 *sin_, c64 *sout, int tid, int nt) {
     constexpr int T = N / R, ITEMS = kSpecL * T, STEP = N / (P * R);
     for (int idx = tid; idx < ITEMS; idx += nt) {
         const int l = idx & (kSpecL - 1), b = idx >> 4;

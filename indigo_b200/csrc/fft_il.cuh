@@ -128,4 +128,36 @@ IB_HD void sense_combine_body(const SenseFftArgs &a, c64 *bufA, c64 *acc, int64_
     }
 }
 
+// Windowed strided pass over 16-line tiles of the interleaved grid (y and z passes of both
+// directions).  Same Stockham stages as fft_pass_body_spec<..., AXIS0 = false>, specialised through
+// IlCtx: full tiles only (inner % 16 == 0), position stride < 2^32 elements.
+struct IlPassArgs {
+    c64 *x;                            // first element of slab 0, transformed in place
+    const c64 *tw;
+    int64_t inner, outer, outer_stride;
+    unsigned pstride;
+    int in0, in1, out0, out1;
+};
+
+template <int N, int R0, int R1, int R2, bool SWAP_IN, bool SWAP_OUT>
+IB_HD void fft_il_pass_body(const IlPassArgs &a, c64 *bufA, int64_t block, int tid, int nt) {
+    constexpr bool THREE = R2 > 1;
+    c64 *bufB = bufA + (size_t)N * kSpecLP;
+    const int64_t tiles = a.inner / kSpecL;
+    const int64_t o = block / tiles, s0 = (block % tiles) * kSpecL;
+    IlCtx<SWAP_IN, SWAP_OUT> c;
+    c.gin = a.x + o * a.outer_stride + s0; c.gout = a.x + o * a.outer_stride + s0;
+    c.tw = a.tw; c.pstride = a.pstride;
+    c.in0 = a.in0; c.inlen = (unsigned)(a.in1 - a.in0); c.out0 = a.out0; c.outlen = (unsigned)(a.out1 - a.out0);
+    spec_stage_lfast<N, R0, 1, true, false, 0, 0>(c, nullptr, bufA, tid, nt);
+    IB_SYNC();
+    if (THREE) {
+        spec_stage_lfast<N, R1, R0, false, false, 0, 0>(c, bufA, bufB, tid, nt);
+        IB_SYNC();
+        spec_stage_lfast<N, THREE ? R2 : R1, R0 * R1, false, true, 0, 0>(c, bufB, nullptr, tid, nt);
+    } else {
+        spec_stage_lfast<N, R1, R0, false, true, 0, 0>(c, bufA, nullptr, tid, nt);
+    }
+}
+
 }  // namespace ib200

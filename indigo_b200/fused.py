@@ -33,7 +33,10 @@ class SenseDevice(object):
     allow_real = True          # use the real-weight packed kernels when the matrix values are real
     long_thresh = 512          # rows of G'^H with more entries than this get a whole CTA each
     sample_tile = (8, 8, 8)    # samples (rows of G') are sorted by the grid tile of this size they fall into
-    staged = -4                # rows_per_group code of ib200_ccsrmm_ilr: shared-memory staged entries, 4 loads in flight
+    # rows_per_group codes of ib200_ccsrmm_ilr (measured on cfg3, profiles/r01_s5_*): shared-memory staged
+    # entries; one coil per lane for the long forward rows, two coils per lane for the short adjoint rows
+    staged_fwd = -41
+    staged_adj = -4
 
     def __init__(self, B, N, coord, maps, oversamp=2.0, weights=None, width=3, n=128):
         from .sense import gridding_matrix_device, _fftc_mod
@@ -131,7 +134,7 @@ class SenseDevice(object):
         G, lib, s = self.G, self.B._lib, self.B._stream
         if self.real:
             lib.ccsrmm_ilr(s, self.M, self.on, self.C, self.nnz, a.real, a.imag, self.g_pk.ptr, self.g_ptr.ptr,
-                           self.grid.ptr, self.C, self.ksp.ptr, self.C, self.g_map.ptr, self.staged, None, 0, 0)
+                           self.grid.ptr, self.C, self.ksp.ptr, self.C, self.g_map.ptr, self.staged_fwd, None, 0, 0)
         else:
             lib.ccsrmm_il(s, self.M, self.on, self.C, self.nnz, a.real, a.imag, G.values.ptr, G.colInds.ptr,
                           G.rowPtrs.ptr, self.grid.ptr, self.C, self.ksp.ptr, self.C, None, 0, None, 0, 0)
@@ -141,7 +144,7 @@ class SenseDevice(object):
         lr = self.longrows.ptr if self.nlong else None
         if self.real:
             lib.ccsrmm_ilr(s, self.kp, self.M, self.C, self.nnz, 1.0, 0.0, self.t_pk.ptr, self.t_ptr.ptr,
-                           self.ksp.ptr, self.C, self.grid.ptr, self.C, self.rowmap.ptr, self.staged, lr, self.nlong,
+                           self.ksp.ptr, self.C, self.grid.ptr, self.C, self.rowmap.ptr, self.staged_adj, lr, self.nlong,
                            self.long_thresh)
         else:
             lib.ccsrmm_il(s, self.kp, self.M, self.C, self.nnz, 1.0, 0.0, self.t_val.ptr, self.t_ind.ptr,

@@ -83,6 +83,25 @@ static int emul_strided(const AxisPlan &ax, c64 *base, int64_t inner, int64_t ou
     k.in0 = in0; k.in1 = in1; k.out0 = out0; k.out1 = out1;
     k.inner = inner; k.outer = outer; k.outer_stride = outer_stride;
     bool done = false;
+    if (inner % kSpecL == 0 && getenv("IB200_FFT_IL_GENERIC") == nullptr) {      // same choice as sense_strided_pass (fft.cu)
+        IlPassArgs a;
+        a.x = base; a.tw = ax.tw_dev; a.inner = inner; a.outer = outer; a.outer_stride = outer_stride;
+        a.pstride = (unsigned)inner; a.in0 = in0; a.in1 = in1; a.out0 = out0; a.out1 = out1;
+#define EMUL_IL(n, r0, r1, r2)                                                                     \
+        if (!done && fft_spec_matches(k, n, r0, r1, r2)) {                                         \
+            done = true;                                                                           \
+            std::vector<c64> sp((size_t)2 * n * kSpecLP + 1);                                      \
+            const int64_t nb = (inner / kSpecL) * outer;                                           \
+            for (int64_t b = 0; b < nb; ++b) {                                                     \
+                if (swap_in)       fft_il_pass_body<n, r0, r1, r2, true, false>(a, sp.data(), b, 0, 1);  \
+                else if (swap_out) fft_il_pass_body<n, r0, r1, r2, false, true>(a, sp.data(), b, 0, 1);  \
+                else               fft_il_pass_body<n, r0, r1, r2, false, false>(a, sp.data(), b, 0, 1); \
+            }                                                                                      \
+        }
+        IB200_FFT_SPEC_LIST(EMUL_IL)
+#undef EMUL_IL
+        if (done) return 0;
+    }
 #define EMUL_SP(n, r0, r1, r2)                                                                     \
     if (!done && fft_spec_matches(k, n, r0, r1, r2)) {                                             \
         done = true;                                                                               \

@@ -111,7 +111,7 @@ def main():
     kref = torch.empty_like(kil); xsave = xil.clone()
     xil.normal_()
     lib.ccsrmm_ilr(s, m, k, C, nnz, 1.0, 0.0, g_pk.data_ptr(), G.rowPtrs.ptr, xil.data_ptr(), C, kref.data_ptr(), C, None, 0, None, 0, 0)
-    for u in (4, 8):
+    for u in (4, 41):
         out["fwd_staged_u%d_ms" % u] = timed(lambda: lib.ccsrmm_ilr(
             s, m, k, C, nnz, 1.0, 0.0, g_pk.data_ptr(), G.rowPtrs.ptr, xil.data_ptr(), C, kil.data_ptr(), C, None, -u, None, 0, 0))
         out["fwd_staged_u%d_relerr" % u] = float((kil - kref).norm() / kref.norm())
@@ -119,7 +119,7 @@ def main():
     xref = torch.empty_like(xil)
     lib.ccsrmm_ilr(s, kp, m, C, nnz, 1.0, 0.0, t_pk.data_ptr(), t_ptr.data_ptr(), kil.data_ptr(), C, xref.data_ptr(), C,
                    rowmap.data_ptr(), 1, longrows.data_ptr(), nlong, args.thresh)
-    for u in (4, 8):
+    for u in (4, 41):
         xil.zero_()
         out["adj_staged_u%d_ms" % u] = timed(lambda: lib.ccsrmm_ilr(
             s, kp, m, C, nnz, 1.0, 0.0, t_pk.data_ptr(), t_ptr.data_ptr(), kil.data_ptr(), C, xil.data_ptr(), C,
@@ -128,7 +128,7 @@ def main():
     # forward with the samples sorted by grid tile (rows permuted at setup, outputs scattered through rowmap)
     xil.normal_()
     lib.ccsrmm_ilr(s, m, k, C, nnz, 1.0, 0.0, g_pk.data_ptr(), G.rowPtrs.ptr, xil.data_ptr(), C, kref.data_ptr(), C, None, 0, None, 0, 0)
-    for stile in ((8, 8, 8), (16, 8, 8), (16, 16, 16)):
+    for stile in ((4, 4, 4), (8, 4, 4), (8, 8, 8)):
         st3 = (ctypes.c_int64 * 3)(*stile)
         lib.grid_tile_rank(s, grid3, st3, None, None, ctypes.byref(padded))
         kp2 = padded.value
@@ -144,9 +144,9 @@ def main():
         torch.cuda.synchronize()
         tag = "x".join(str(v) for v in stile)
         out["sort_rows_%s_s" % tag] = round(time.time() - t0, 3)
-        for mode in (0, -4):
+        for mode in (-41, -4):
             kil.zero_()
-            out["fwd_sorted_%s_%s_ms" % (tag, "staged" if mode else "plain")] = timed(lambda: lib.ccsrmm_ilr(
+            out["fwd_sorted_%s_%s_ms" % (tag, "vc2" if mode == -4 else "vc1")] = timed(lambda: lib.ccsrmm_ilr(
                 s, m, k, C, nnz, 1.0, 0.0, g_pk2.data_ptr(), g_ptr2.data_ptr(), xil.data_ptr(), C, kil.data_ptr(), C,
                 g_map.data_ptr(), mode, None, 0, 0))
             out["fwd_sorted_%s_relerr" % tag] = float((kil - kref).norm() / kref.norm())
