@@ -61,6 +61,21 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(workload, world, call):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant step, from the committed
+    `ncu --set full` capture of the same build and workload (profiles/traffic.json); None when no capture
+    matches (other workloads, other GPU counts)."""
+    path = os.path.join(REPO, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    table = json.load(open(path))
+    entry = table.get("%s:%d" % (workload, world), {})
+    for prefix, rec in entry.items():
+        if call.startswith(prefix):
+            return rec["bytes"], rec["source"]
+    return None, None
+
+
 # --------------------------------------------------------------------------- clocks
 class ClockSampler(object):
     """nvidia-smi clocks line of B200_PROFILING.md, sampled every 200 ms while the timed region runs."""
@@ -283,6 +298,7 @@ def run_ours(args):
     calls = timer.summary(peak)
     if rank == 0:
         dom = calls[0]
+        traffic, traffic_src = measured_traffic(args.workload, world, dom["call"])
         line = {
             "metric": "SENSE-NUFFT A^H A applies/sec", "value": args.steps / (total_ms * 1e-3), "unit": "applies/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -299,7 +315,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(x_h.nbytes), "d2h_bytes_per_step": int(y_h.nbytes)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom["call"], "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
-                         "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
+                         "frac": dom["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "share_of_step": dom["share"], "launches_per_call": dom["launches_per_call"]},
             "calls": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in c.items()} for c in calls],
             "clocks": clk, "setup_s": round(setup_s, 1),

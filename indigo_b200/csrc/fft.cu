@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(sense_x_threads(N), 2) sense_combine_kernel(co
 template <int N, int R0, int R1, int R2>
 static int launch_sense_x(cudaStream_t s, bool combine, const SenseFftArgs &a) {
     static bool attr_done[2][64] = {{false}};
-    const size_t smem = (size_t)2 * N * kSpecLP * sizeof(c64) + (combine ? (size_t)a.N0 * sizeof(c64) : 0);
+    const size_t smem = (size_t)2 * N * kSpecLP * sizeof(c64) + (combine ? (size_t)a.N0 * sense_x_tile(a.C).YY * sizeof(c64) : 0);
     IB200_REQUIRE((int64_t)smem <= smem_optin(), "sense x pass: tile does not fit shared memory");
     int dev = 0;
     IB200_TRY(cudaGetDevice(&dev));
@@ -111,7 +111,7 @@ static int launch_sense_x(cudaStream_t s, bool combine, const SenseFftArgs &a) {
         else         IB200_TRY(cudaFuncSetAttribute(sense_expand_kernel<N, R0, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin()));
         attr_done[combine ? 1 : 0][dev & 63] = true;
     }
-    const int64_t blocks = (int64_t)a.N1 * a.N2;
+    const int64_t blocks = sense_x_blocks(a.N1, a.N2, a.C);
     IB200_REQUIRE(blocks < (1LL << 31), "sense x pass: too many rows for one launch");
     if (combine) sense_combine_kernel<N, R0, R1, R2><<<(unsigned)blocks, sense_x_threads(N), smem, s>>>(a);
     else         sense_expand_kernel<N, R0, R1, R2><<<(unsigned)blocks, sense_x_threads(N), smem, s>>>(a);

@@ -154,11 +154,15 @@ struct FftCtx {
     int swap_in, swap_out, conj_in, conj_out;
     int in0, in1;          // positions outside [in0, in1) read as zero without touching memory (pruned input)
     int out0, out1;        // positions outside [out0, out1) are not stored (pruned output)
+    // two-level line addressing: line l sits at (l & lmask)*gstride_l + (l >> lshift)*gstride_l2
+    // (tiles made of a few coils of several neighbouring rows, fft_il.cuh); default: one level
+    int lmask = 0x7fffffff, lshift = 31;
+    int64_t gstride_l2 = 0;
 };
 
 IB_HD c64 fft_gload(const FftCtx &c, int l, int j) {
     if (j < c.in0 || j >= c.in1) return h_mk(0.f, 0.f);
-    const int64_t off = (int64_t)l * c.gstride_l + (int64_t)j * c.gstride_j;
+    const int64_t off = (int64_t)(l & c.lmask) * c.gstride_l + (int64_t)(l >> c.lshift) * c.gstride_l2 + (int64_t)j * c.gstride_j;
     c64 v = c.gin[off];
     if (c.din) { const c64 d = c.din[off]; v = c.conj_in ? h_mulc(v, d) : h_mul(v, d); }
     return c.swap_in ? h_swap(v) : v;
@@ -166,7 +170,7 @@ IB_HD c64 fft_gload(const FftCtx &c, int l, int j) {
 
 IB_HD void fft_gstore(const FftCtx &c, int l, int j, c64 v) {
     if (j < c.out0 || j >= c.out1) return;
-    const int64_t off = (int64_t)l * c.gstride_l + (int64_t)j * c.gstride_j;
+    const int64_t off = (int64_t)(l & c.lmask) * c.gstride_l + (int64_t)(l >> c.lshift) * c.gstride_l2 + (int64_t)j * c.gstride_j;
     if (c.swap_out) v = h_swap(v);
     if (c.dout) { const c64 d = c.dout[off]; v = c.conj_out ? h_mulc(v, d) : h_mul(v, d); }
     c.gout[off] = v;

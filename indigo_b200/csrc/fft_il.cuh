@@ -32,13 +32,34 @@ struct SenseFftArgs {
     int beta_zero;
 };
 
+// Tile geometry of the x passes: 16 lines = YY neighbouring image rows x CT coils.  With 16 or more
+// coils a tile is one row and the coils go in chunks of 16; with 2, 4 or 8 coils per GPU (coil
+// sharding) a tile takes 8, 4 or 2 rows so that all 16 lines stay busy.
+struct XTile { int CT, YY, shift; };
+IB_HD XTile sense_x_tile(int C) {
+    XTile t;
+    t.CT = C < kSpecL ? C : kSpecL; t.YY = 1; t.shift = 31;
+    if (C == 1 || C == 2 || C == 4 || C == 8) {
+        t.YY = kSpecL / C;
+        t.shift = C == 1 ? 0 : C == 2 ? 1 : C == 4 ? 2 : 3;
+    }
+    return t;
+}
+IB_HD int64_t sense_x_blocks(int N1, int N2, int C) {
+    const XTile t = sense_x_tile(C);
+    return (int64_t)((N1 + t.YY - 1) / t.YY) * N2;
+}
+
 // x pass of the forward transform: grid[z+off2][y+off1][:][c] = FFT_x( zpad( img[:, y, z] * pf[., c] ) )
-// one CTA per image row (y, z); coils in chunks of 16 lines.
+// one CTA per group of YY image rows (y .. y+YY-1, z); coils in chunks of 16 lines when C > 16.
 template <int N, int R0, int R1, int R2>
 IB_HD void sense_expand_body(const SenseFftArgs &a, c64 *bufA, int64_t block, int tid, int nt) {
     constexpr bool THREE = R2 > 1;
     c64 *bufB = bufA + (size_t)N * kSpecLP;
-    const int y = (int)(block % a.N1), z = (int)(block / a.N1);
+    const XTile t = sense_x_tile(a.C);
+    const int ygroups = (a.N1 + t.YY - 1) / t.YY;
+    const int y = (int)(block % ygroups) * t.YY, z = (int)(block / ygroups);
+    const int rows = a.N1 - y < t.YY ? a.N1 - y : t.YY;
     const int64_t vox0 = ((int64_t)z * a.N1 + y) * a.N0;
     FftCtx c;
     c.n = N; c.L = kSpecL; c.log2L = 4; c.LP = kSpecLP; c.tw = a.tw;
@@ -46,17 +67,21 @@ IB_HD void sense_expand_body(const SenseFftArgs &a, c64 *bufA, int64_t block, in
     c.din = c.dout = nullptr;
     c.in0 = 0; c.in1 = N; c.out0 = 0; c.out1 = N;
     c.gstride_j = a.C; c.gstride_l = 1;
+    if (t.YY > 1) { c.lmask = t.CT - 1; c.lshift = t.shift; c.gstride_l2 = (int64_t)a.n0 * a.C; }
     c.gin = nullptr;
     const int64_t row = ((int64_t)(z + a.off2) * a.n1 + (y + a.off1)) * (int64_t)a.n0 * a.C;
     for (int c0 = 0; c0 < a.C; c0 += kSpecL) {
-        c.nl = a.C - c0 < kSpecL ? a.C - c0 : kSpecL;
+        c.nl = t.YY > 1 ? rows * t.CT : (a.C - c0 < kSpecL ? a.C - c0 : kSpecL);
         c.gout = a.grid + row + c0;
         for (int idx = tid; idx < N * kSpecL; idx += nt) {
             const int l = idx & (kSpecL - 1), pos = idx >> 4;
             if (l >= c.nl) continue;
             const int j = pos - a.off0;
             c64 v = h_mk(0.f, 0.f);
-            if (j >= 0 && j < a.N0) v = h_mul(a.img[vox0 + j], a.pf[(vox0 + j) * a.C + c0 + l]);
+            if (j >= 0 && j < a.N0) {
+                const int64_t vox = vox0 + (int64_t)(l >> c.lshift) * a.N0 + j;
+                v = h_mul(a.img[vox], a.pf[vox * a.C + c0 + (l & c.lmask)]);
+            }
             bufA[spec_addr<0>(pos, l)] = v;
         }
         IB_SYNC();
@@ -77,12 +102,15 @@ IB_HD void sense_expand_body(const SenseFftArgs &a, c64 *bufA, int64_t block, in
 //   img_out[:, y, z] = alpha * sum_c conj(pf[., c]) * crop( IFFT_x( grid[z+off2][y+off1][:][c] ) ) + beta * img_out
 // The re/im swap that turns the forward butterflies into the inverse transform was applied on the
 // load of the first inverse pass (z); this is the last pass, so it swaps back before the product.
-// `acc` is N0 complex words of shared memory.
+// `acc` is YY*N0 complex words of shared memory.
 template <int N, int R0, int R1, int R2>
 IB_HD void sense_combine_body(const SenseFftArgs &a, c64 *bufA, c64 *acc, int64_t block, int tid, int nt) {
     constexpr bool THREE = R2 > 1;
     c64 *bufB = bufA + (size_t)N * kSpecLP;
-    const int y = (int)(block % a.N1), z = (int)(block / a.N1);
+    const XTile t = sense_x_tile(a.C);
+    const int ygroups = (a.N1 + t.YY - 1) / t.YY;
+    const int y = (int)(block % ygroups) * t.YY, z = (int)(block / ygroups);
+    const int rows = a.N1 - y < t.YY ? a.N1 - y : t.YY;
     const int64_t vox0 = ((int64_t)z * a.N1 + y) * a.N0;
     FftCtx c;
     c.n = N; c.L = kSpecL; c.log2L = 4; c.LP = kSpecLP; c.tw = a.tw;
@@ -90,10 +118,12 @@ IB_HD void sense_combine_body(const SenseFftArgs &a, c64 *bufA, c64 *acc, int64_
     c.din = c.dout = nullptr;
     c.in0 = 0; c.in1 = N; c.out0 = 0; c.out1 = N;
     c.gstride_j = a.C; c.gstride_l = 1;
+    if (t.YY > 1) { c.lmask = t.CT - 1; c.lshift = t.shift; c.gstride_l2 = (int64_t)a.n0 * a.C; }
     c.gout = nullptr;
     const int64_t row = ((int64_t)(z + a.off2) * a.n1 + (y + a.off1)) * (int64_t)a.n0 * a.C;
     for (int c0 = 0; c0 < a.C; c0 += kSpecL) {
-        c.nl = a.C - c0 < kSpecL ? a.C - c0 : kSpecL;
+        c.nl = t.YY > 1 ? rows * t.CT : (a.C - c0 < kSpecL ? a.C - c0 : kSpecL);
+        const int ncl = t.YY > 1 ? t.CT : c.nl;                   // coils of one row in this tile
         c.gin = a.grid + row + c0;
         spec_stage_lfast<N, R0, 1, true, false, 0, 0>(c, nullptr, bufA, tid, nt);
         IB_SYNC();
@@ -110,21 +140,23 @@ IB_HD void sense_combine_body(const SenseFftArgs &a, c64 *bufA, c64 *acc, int64_
             const int l = idx & (kSpecL - 1), j = idx >> 4;
             if (l >= c.nl) continue;
             const int at = spec_addr<0>(j + a.off0, l);
-            res[at] = h_mulc(h_swap(res[at]), a.pf[(vox0 + j) * a.C + c0 + l]);
+            const int64_t vox = vox0 + (int64_t)(l >> c.lshift) * a.N0 + j;
+            res[at] = h_mulc(h_swap(res[at]), a.pf[vox * a.C + c0 + (l & c.lmask)]);
         }
         IB_SYNC();
-        // ... and fold the coils of each position
-        for (int j = tid; j < a.N0; j += nt) {
-            c64 s = c0 == 0 ? h_mk(0.f, 0.f) : acc[j];
-            for (int l = 0; l < c.nl; ++l) s = h_add(s, res[spec_addr<0>(j + a.off0, l)]);
-            acc[j] = s;
+        // ... and fold the coils of each (row, position)
+        for (int i = tid; i < rows * a.N0; i += nt) {
+            const int yy = i / a.N0, j = i - yy * a.N0;
+            c64 s = c0 == 0 ? h_mk(0.f, 0.f) : acc[i];
+            for (int l = 0; l < ncl; ++l) s = h_add(s, res[spec_addr<0>(j + a.off0, yy * ncl + l)]);
+            acc[i] = s;
         }
         IB_SYNC();
     }
-    for (int j = tid; j < a.N0; j += nt) {
-        c64 v = h_mul(a.alpha, acc[j]);
-        if (!a.beta_zero) v = h_add(v, h_mul(a.beta, a.img_out[vox0 + j]));
-        a.img_out[vox0 + j] = v;
+    for (int i = tid; i < rows * a.N0; i += nt) {
+        c64 v = h_mul(a.alpha, acc[i]);
+        if (!a.beta_zero) v = h_add(v, h_mul(a.beta, a.img_out[vox0 + i]));
+        a.img_out[vox0 + i] = v;
     }
 }
 

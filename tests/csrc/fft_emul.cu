@@ -136,7 +136,7 @@ extern "C" int emul_sense(const int64_t *N, const int64_t *oN, int64_t C, int wh
         if (!done && fft_spec_matches(k0, n, r0, r1, r2)) {                                        \
             done = true;                                                                           \
             std::vector<c64> sp((size_t)2 * n * kSpecLP + 1);                                      \
-            for (int64_t b = 0; b < N[1] * N[2]; ++b) sense_expand_body<n, r0, r1, r2>(a, sp.data(), b, 0, 1); \
+            for (int64_t b = 0; b < sense_x_blocks((int)N[1], (int)N[2], (int)C); ++b) sense_expand_body<n, r0, r1, r2>(a, sp.data(), b, 0, 1); \
         }
         IB200_FFT_SPEC_LIST(EMUL_X)
 #undef EMUL_X
@@ -153,8 +153,8 @@ extern "C" int emul_sense(const int64_t *N, const int64_t *oN, int64_t C, int wh
 #define EMUL_C(n, r0, r1, r2)                                                                      \
     if (!done && fft_spec_matches(k0, n, r0, r1, r2)) {                                            \
         done = true;                                                                               \
-        std::vector<c64> sp((size_t)2 * n * kSpecLP + 1), acc((size_t)N[0] + 1);                   \
-        for (int64_t b = 0; b < N[1] * N[2]; ++b) sense_combine_body<n, r0, r1, r2>(a, sp.data(), acc.data(), b, 0, 1); \
+        std::vector<c64> sp((size_t)2 * n * kSpecLP + 1), acc((size_t)N[0] * kSpecL + 1);                   \
+        for (int64_t b = 0; b < sense_x_blocks((int)N[1], (int)N[2], (int)C); ++b) sense_combine_body<n, r0, r1, r2>(a, sp.data(), acc.data(), b, 0, 1); \
     }
     IB200_FFT_SPEC_LIST(EMUL_C)
 #undef EMUL_C

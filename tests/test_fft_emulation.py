@@ -90,7 +90,9 @@ def _crand(rs, *shape):
 
 
 @pytest.mark.parametrize("N,oN,C", [((16, 16, 16), (32, 32, 32), 16), ((16, 26, 16), (32, 52, 32), 4),
-                                    ((13, 20, 16), (32, 32, 52), 20), ((32, 16, 26), (64, 32, 52), 3)])
+                                    ((13, 20, 16), (32, 32, 52), 20), ((32, 16, 26), (64, 32, 52), 3),
+                                    ((16, 13, 8), (32, 32, 32), 2), ((16, 15, 4), (32, 32, 32), 8),
+                                    ((16, 16, 5), (32, 32, 32), 1)])
 def test_fused_sense_expand_and_combine(emul_sense, N, oN, C):
     """grid[z][y][x][c] = FFT3(zpad(pf*img)) and img = alpha*sum_c conj(pf)*crop(IFFT3_unscaled(grid)) + beta*img,
     against numpy on the same data (zero-pad placement of Backend.Zpad 'center', backend.py:371-387)."""

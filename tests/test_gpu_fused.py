@@ -31,7 +31,8 @@ def relerr(a, b):
 
 
 CASES = [((16, 16, 16), 4, "random", True), ((16, 26, 16), 3, "random", False), ((26, 26, 26), 16, "koosh", True),
-         ((16, 16, 26), 20, "random", True), ((32, 16, 16), 1, "koosh", False)]
+         ((16, 16, 26), 20, "random", True), ((32, 16, 16), 1, "koosh", False),
+         ((16, 26, 16), 2, "random", True), ((26, 16, 16), 8, "koosh", False), ((16, 26, 16), 4, "random", False)]
 
 
 def _setup(N, C, traj, weighted, seed=0):
