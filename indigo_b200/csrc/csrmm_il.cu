@@ -341,6 +341,37 @@ __global__ void __launch_bounds__(256) long_rows_kernel(int64_t m, const int32_t
     }
 }
 
+// The long-row kernel is latency bound (one CTA per row, few CTAs) and independent of the main
+// gather: it runs on a side stream, forked from and joined back into the caller's stream with
+// events, so that both kernels share the SMs instead of running back to back.
+struct SideStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    int dev = -1;
+};
+static thread_local SideStream g_side;
+
+static int side_stream_begin(cudaStream_t main, cudaStream_t *side) {
+    int dev = 0;
+    IB200_TRY(cudaGetDevice(&dev));
+    if (g_side.dev != dev) {
+        IB200_TRY(cudaStreamCreateWithFlags(&g_side.s, cudaStreamNonBlocking));
+        IB200_TRY(cudaEventCreateWithFlags(&g_side.fork, cudaEventDisableTiming));
+        IB200_TRY(cudaEventCreateWithFlags(&g_side.join, cudaEventDisableTiming));
+        g_side.dev = dev;
+    }
+    IB200_TRY(cudaEventRecord(g_side.fork, main));
+    IB200_TRY(cudaStreamWaitEvent(g_side.s, g_side.fork, 0));
+    *side = g_side.s;
+    return 0;
+}
+
+static int side_stream_end(cudaStream_t main) {
+    IB200_TRY(cudaEventRecord(g_side.join, g_side.s));
+    IB200_TRY(cudaStreamWaitEvent(main, g_side.join, 0));
+    return 0;
+}
+
 template <bool PACKED>
 static int launch_long(cudaStream_t s, int CL, int nlong, const int32_t *longrows, int C, c64 alpha, const void *ent,
                        const c64 *vals, const int32_t *colind, const int32_t *rowptr, const c64 *Xil, int64_t xpitch,
@@ -572,6 +603,10 @@ __global__ void __launch_bounds__(256) tile_rank_kernel(int n0, int n1, int n2, 
 static int pow2_ceil(int64_t v) { int p = 1; while (p < v) p <<= 1; return p; }
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
+int ilr_main(cudaStream_t s, int staged, int CL, double avg, int rows_per_group, int64_t m, int64_t ncols, c64 alpha,
+             const void *packed, const int32_t *rowptr, const void *Xil, int64_t xpitch, void *Yil, int64_t ypitch,
+             const int32_t *rowmap, int long_thresh);
+
 }  // namespace ib200
 
 using namespace ib200;
@@ -738,16 +773,36 @@ int ib200_ccsrmm_ilr(void *stream, int64_t m, int64_t k, int64_t ncols, int64_t 
     IB200_REQUIRE(rows_per_group >= 0 && rows_per_group <= 4096, "rows_per_group out of range");
     const int CL = pow2_ceil(ncols);
     const double avg = (double)nnz / (double)m;
+    const c64 alpha = mk(ar, ai);
+    cudaStream_t s = as_stream(stream);
+    int rc = 0;
+    if (nlong > 0) {
+        cudaStream_t side = nullptr;
+        rc = side_stream_begin(s, &side);
+        if (rc) return rc;
+        rc = launch_long<true>(side, CL, nlong, longrows, (int)ncols, alpha, packed, nullptr, nullptr, rowptr,
+                               (const c64 *)Xil, xpitch, (c64 *)Yil, ypitch, rowmap);
+        if (rc) return rc;
+        rc = ilr_main(s, staged, CL, avg, rows_per_group, m, ncols, alpha, packed, rowptr, Xil, xpitch, Yil, ypitch, rowmap,
+                      long_thresh);
+        const int rc2 = side_stream_end(s);
+        return rc ? rc : rc2;
+    }
+    return ilr_main(s, staged, CL, avg, rows_per_group, m, ncols, alpha, packed, rowptr, Xil, xpitch, Yil, ypitch, rowmap,
+                    long_thresh);
+}
+
+}  // extern "C"
+
+namespace ib200 {
+int ilr_main(cudaStream_t s, int staged, int CL, double avg, int rows_per_group, int64_t m, int64_t ncols, c64 alpha,
+             const void *packed, const int32_t *rowptr, const void *Xil, int64_t xpitch, void *Yil, int64_t ypitch,
+             const int32_t *rowmap, int long_thresh) {
     int GL = CL;
     while (GL < 32 && avg >= 4.0 * GL) GL <<= 1;                 // slots only pay when each gets >= 4 entries
     int rpg = rows_per_group;
     if (rpg == 0) rpg = avg >= 32 ? (32 * GL) / 256 : 1;
     if (rpg < 1) rpg = 1;
-    const c64 alpha = mk(ar, ai);
-    cudaStream_t s = as_stream(stream);
-    int rc = launch_long<true>(s, CL, nlong, longrows, (int)ncols, alpha, packed, nullptr, nullptr, rowptr,
-                               (const c64 *)Xil, xpitch, (c64 *)Yil, ypitch, rowmap);
-    if (rc) return rc;
     if (staged) {                                                  // shared-memory staged entries, 4 rows per group
         // two coils per lane (16-byte operand loads) whenever the layout allows it
         const bool vec2 = staged != 41 && ncols % 2 == 0 && xpitch % 2 == 0 && ypitch % 2 == 0 &&
@@ -783,4 +838,4 @@ int ib200_ccsrmm_ilr(void *stream, int64_t m, int64_t k, int64_t ncols, int64_t 
     return IB200_E_UNSUPPORTED;
 }
 
-}  // extern "C"
+}  // namespace ib200
