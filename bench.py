@@ -220,6 +220,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     wl = WORKLOADS[args.workload]
     N, C = wl["N"], wl["C"]
+    if getattr(args, "coils", 0):
+        C = args.coils
+        wl = dict(wl, desc=wl["desc"] + " [DEVELOPMENT RUN with %d coils, not the named configuration]" % C)
     if C % world:
         raise SystemExit("coil count %d not divisible by %d ranks" % (C, world))
     B = B200Backend(local)
@@ -418,6 +421,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--coils", type=int, default=0,
+                    help="development only: override the workload's coil count (e.g. 2 = the per-GPU shard of cfg3 at 8 GPUs)")
     ap.add_argument("--tree", default="fused", choices=["fused", "o3"],
                     help="fused: backend-specific fused recipe (default); o3: the reference's six-call -O3 tree")
     args = ap.parse_args()

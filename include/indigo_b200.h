@@ -151,6 +151,24 @@ int ib200_csr_long_rows(void *stream, int64_t m, const int32_t *rowptr, int thre
                         int *host_count);
 int ib200_grid_tile_rank(void *stream, const int64_t grid[3], const int64_t tile[3], int32_t *colrank, int32_t *rowmap,
                          int64_t *padded_rows);
+/* Separable Kaiser-Bessel gridding (the product ccsrmm(G') of the -O3 SENSE tree, SURVEY.md 3.1,
+ * without a stored matrix).  interp.py:19-60 emits every value of a row as li(x)*li(y)*li(z) and the
+ * -O2 recipe multiplies in the centring phase and the grid scale (backend.py:349-364), all of which
+ * factor over the axes.  ib200_kb_records writes one record of ib200_kb_record_bytes() (96) bytes per
+ * sample: 3 x 6 float32 weights (f0/f1/f2 = per-axis real factors of mod*scale, indexed by grid
+ * coordinate; rowweight = optional per-sample weight), the first tap of each axis wrapped into the grid,
+ * the tap counts and the output row.  Record r describes sample perm[r] (perm NULL: identity), so the
+ * records can be stored in the tile-sorted order ib200_csr_permute_rows produces while results land
+ * in the original rows.  *host_flag != 0 on return means some sample needs more than 6 taps on an axis
+ * (or the grid is smaller than the kernel): the caller must stay on the stored-matrix path.
+ * Synchronises.  ib200_kb_gather computes Yil[out][c] = alpha * sum_taps w * Xil[tap][c] for ncols
+ * interleaved columns (Xil = grid[z][y][x][c] with `xpitch` elements per grid point). */
+int ib200_kb_record_bytes(void);
+int ib200_kb_records(void *stream, int64_t m, const double *coord, const int64_t grid[3], double width,
+                     const double *table, int ntable, const float *rowweight, const float *f0, const float *f1,
+                     const float *f2, const int32_t *perm, void *records, int *host_flag);
+int ib200_kb_gather(void *stream, int64_t m, int64_t ncols, float alpha_re, float alpha_im, const void *records,
+                    const void *grid_il, int64_t xpitch, const int64_t grid[3], void *Yil, int64_t ypitch);
 /* The inspector of _customcpu.c:179-215 on the device: out = {rows with >=1
  * entry, columns with >=1 entry, exwrite flag, max entries in one column}.
  * `work` is k int32 of device scratch.  Synchronises `stream`. */

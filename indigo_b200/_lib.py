@@ -43,6 +43,10 @@ SIGNATURES = {
     "ib200_csr_pack_real": (_i, [_vp, _i64, _vp, _vp, _vp, POINTER(c_float)]),
     "ib200_ccsrmm_ilr": (_i, [_vp, _i64, _i64, _i64, _i64, _f, _f, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i,
                               _vp, _i, _i]),
+    "ib200_kb_record_bytes": (_i, []),
+    "ib200_kb_records": (_i, [_vp, _i64, _vp, POINTER(_i64), c_double, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp,
+                              POINTER(_i)]),
+    "ib200_kb_gather": (_i, [_vp, _i64, _i64, _f, _f, _vp, _vp, _i64, POINTER(_i64), _vp, _i64]),
     "ib200_grid_tile_rank": (_i, [_vp, POINTER(_i64), POINTER(_i64), _vp, _vp, POINTER(_i64)]),
     "ib200_csr_inspect": (_i, [_vp, _i64, _i64, _vp, _vp, _vp, POINTER(_i64)]),
     "ib200_csr_transpose_conj": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -69,7 +73,7 @@ SIGNATURES = {
 
 # entry points that return something other than a status code
 _NO_STATUS = {"ib200_last_error", "ib200_version", "ib200_launch_count", "ib200_launch_count_reset",
-              "ib200_fft_plan_describe"}
+              "ib200_fft_plan_describe", "ib200_kb_record_bytes"}
 
 
 class Library(object):

@@ -16,6 +16,7 @@
 // float64 weight arithmetic without FMA contraction and are bit-identical
 // whenever no taps alias (grid extent >= taps), else equal to rounding.
 #include "common.cuh"
+#include "kb.cuh"
 
 namespace ib200 {
 
@@ -26,15 +27,6 @@ struct AxisTaps {
     int idx[kMaxTaps];     // ascending
     double w[kMaxTaps];
 };
-
-// interp.py:9-15 (lin_interp) with every operation individually rounded
-__device__ __forceinline__ double kb_lookup(const double *__restrict__ table, int ntab, double x) {
-    if (x >= 1.0) return 0.0;
-    const double xs = __dmul_rn(x, (double)(ntab - 1));
-    const int i = (int)xs;
-    const double frac = __dsub_rn(xs, (double)i);
-    return __dadd_rn(__dmul_rn(__dsub_rn(1.0, frac), table[i]), __dmul_rn(frac, table[i + 1]));
-}
 
 // taps of one axis: range(ceil(pos-width), floor(pos+width)), interp.py:27-37
 __device__ __forceinline__ void axis_taps(double coord, int N, double width, const double *__restrict__ table,

@@ -1,0 +1,301 @@
+// Separable Kaiser-Bessel gridding gather: the forward interpolation grid -> samples of the fused
+// SENSE recipe without a stored matrix.
+//
+// Reference being replaced: the product ccsrmm(G') of the -O3 tree, where
+// G' = interp * mod * scale is the CSR matrix that indigo/interp.py:19-80 emits tap by tap:
+// value(sample, tap) = li(x) * li(y) * li(z) (interp.py:44-59) times the centring phase and the
+// 1/sqrt(prod oN) scale of backend.py:349-364, which the -O2 recipe folds in (transforms.py:86-96).
+// Every factor is a product over the three axes, so a row of G' is the outer product of three
+// short vectors.  A stored entry costs 8-12 bytes of HBM traffic and one extra load per tap; a
+// record of 3 x 6 weights + 3 base indices costs 96 bytes per SAMPLE instead of 1000-1500 bytes,
+// and the tap addresses follow from the base indices by adds ("structured KB
+// layout", the re-layout that keeps coil sharding from re-reading a 10 GB matrix on every GPU).
+//
+// Parity: weights are the reference's float64 table interpolation (kb.cuh, same arithmetic as the
+// CSR builder) rounded to float32 per axis, times the per-axis real centring factors; the product
+// of the three differs from the reference's float32 value by a few ulp (tests/test_gpu_fused.py
+// compares against the CSR product and the numpy oracle).  Only real-valued G' (grid extents that
+// make the centring phase +-1) and kernels of at most 6 taps per axis are served; anything else
+// stays on the stored-matrix path.
+#include "common.cuh"
+#include "kb.cuh"
+
+namespace ib200 {
+
+static const int kKbTaps = 6;
+
+struct __align__(16) KbRecord {
+    float wx[kKbTaps], wy[kKbTaps], wz[kKbTaps];   // per-axis weights (row weight and scale folded into wz)
+    int32_t ix0, iy0, iz0;                         // first tap per axis, wrapped into [0, n)
+    int32_t out;                                   // output row (original sample index)
+    int32_t ntaps;                                 // nx | ny << 8 | nz << 16
+    int32_t pad;
+};
+static_assert(sizeof(KbRecord) == 96, "KbRecord must be 6 x 16 bytes");
+
+// record r describes sample perm[r] (perm = NULL: identity)
+__global__ void __launch_bounds__(128) kb_records_kernel(int64_t m, const double *__restrict__ coord, int N0, int N1,
+                                                         int N2, double width, const double *__restrict__ table,
+                                                         int ntab, const float *__restrict__ rowweight,
+                                                         const float *__restrict__ f0, const float *__restrict__ f1,
+                                                         const float *__restrict__ f2,
+                                                         const int32_t *__restrict__ perm,
+                                                         KbRecord *__restrict__ rec, int *flag) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    const int64_t i = perm ? (int64_t)perm[r] : r;
+    KbRecord q;
+    int cnt[3], first[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const int N = d == 0 ? N0 : d == 1 ? N1 : N2;
+        const float *f = d == 0 ? f0 : d == 1 ? f1 : f2;
+        float *w = d == 0 ? q.wx : d == 1 ? q.wy : q.wz;
+        // taps range(ceil(pos - width), floor(pos + width)), interp.py:27-37
+        const double pos = __dadd_rn(__dmul_rn((double)N, coord[3 * i + d]), (double)(N / 2));
+        const int start = (int)ceil(__dsub_rn(pos, width));
+        const int end = (int)floor(__dadd_rn(pos, width));
+        int n = end - start;
+        if (n < 0 || n > kKbTaps || n > N) { atomicOr(flag, 1); n = n < 0 ? 0 : (N < kKbTaps ? N : kKbTaps); }
+        int j = start % N; if (j < 0) j += N;
+        first[d] = j; cnt[d] = n;
+#pragma unroll
+        for (int t = 0; t < kKbTaps; ++t) {
+            float v = 0.f;
+            if (t < n) {
+                const double wv = kb_lookup(table, ntab, fabs(__dsub_rn((double)(start + t), pos)) / width);
+                v = __fmul_rn((float)wv, f[j]);
+            }
+            w[t] = v;
+            if (++j >= N) j = 0;
+        }
+    }
+    if (rowweight) {
+        const float rw = rowweight[i];
+#pragma unroll
+        for (int t = 0; t < kKbTaps; ++t) q.wz[t] = __fmul_rn(rw, q.wz[t]);
+    }
+    q.ix0 = first[0]; q.iy0 = first[1]; q.iz0 = first[2];
+    q.out = (int32_t)i;
+    q.ntaps = cnt[0] | (cnt[1] << 8) | (cnt[2] << 16);
+    q.pad = 0;
+    rec[r] = q;
+}
+
+// VC coils per lane: one 8-byte or one 16-byte load per tap
+template <int VC> struct KbVec;
+template <> struct KbVec<1> {
+    float x[1], y[1];
+    __device__ __forceinline__ void load(const char *p) { const float2 v = __ldg(reinterpret_cast<const float2 *>(p)); x[0] = v.x; y[0] = v.y; }
+};
+template <> struct KbVec<2> {
+    float x[2], y[2];
+    __device__ __forceinline__ void load(const char *p) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(p)); x[0] = v.x; y[0] = v.y; x[1] = v.z; y[1] = v.w;
+    }
+};
+
+// one (z, y) row of taps: weighted sum over the x taps, folded into the accumulator with wjk = wz*wy.
+// DENSE: the x taps are consecutive grid points (no wrap-around in this warp) and the pitch of a
+// grid point is the compile-time constant PITCH, so the tap addresses are immediates.
+template <int VC, bool DENSE, int PITCH>
+__device__ __forceinline__ void kb_row(const char *rp, const uint32_t (&xo)[kKbTaps], const float (&wx)[kKbTaps],
+                                       bool sixth, float wjk, float (&ax)[VC], float (&ay)[VC]) {
+    KbVec<VC> q[kKbTaps];
+    const char *r0 = rp + xo[0];
+#pragma unroll
+    for (int t = 0; t < kKbTaps - 1; ++t) q[t].load(DENSE ? r0 + t * PITCH : rp + xo[t]);
+    float tx[VC], ty[VC];
+#pragma unroll
+    for (int v = 0; v < VC; ++v) { tx[v] = wx[0] * q[0].x[v]; ty[v] = wx[0] * q[0].y[v]; }
+#pragma unroll
+    for (int t = 1; t < kKbTaps - 1; ++t)
+#pragma unroll
+        for (int v = 0; v < VC; ++v) { tx[v] = fmaf(wx[t], q[t].x[v], tx[v]); ty[v] = fmaf(wx[t], q[t].y[v], ty[v]); }
+    if (sixth) {                                                     // warp-uniform, rare
+        q[kKbTaps - 1].load(DENSE ? r0 + (kKbTaps - 1) * PITCH : rp + xo[kKbTaps - 1]);
+#pragma unroll
+        for (int v = 0; v < VC; ++v) {
+            tx[v] = fmaf(wx[kKbTaps - 1], q[kKbTaps - 1].x[v], tx[v]);
+            ty[v] = fmaf(wx[kKbTaps - 1], q[kKbTaps - 1].y[v], ty[v]);
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < VC; ++v) { ax[v] = fmaf(wjk, tx[v], ax[v]); ay[v] = fmaf(wjk, ty[v], ay[v]); }
+}
+
+// Y[out(r)*ypitch + c] = alpha * sum_{k,j,i} wz[k] wy[j] wx[i] * grid[iz_k][iy_j][ix_i][c]
+//
+// CL lanes per sample (VC coils each), 32/CL samples per warp; a warp walks `iters` batches of
+// consecutive records, i.e. neighbouring samples of one grid tile when the records were sorted by
+// tile.  The x taps of one (z, y) row are issued together (5-6 independent loads per lane), their
+// weighted sum is folded into the accumulator with the row's wz*wy.  Trip counts are the maximum
+// over the samples of the warp (5 taps per axis except for samples that sit exactly on a grid
+// line, whose sixth tap has weight zero), so control flow is warp-uniform.
+template <int CL, int VC>
+__global__ void __launch_bounds__(256, 3) kb_gather_kernel(int64_t m, int C, c64 alpha, const KbRecord *__restrict__ rec,
+                                                           const c64 *__restrict__ grid, uint32_t pitch, int n0, int n1,
+                                                           int n2, c64 *__restrict__ Y, int64_t ypitch, int iters) {
+    constexpr int SPW = 32 / CL;
+    constexpr int PITCH = CL * VC * 8;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = (int)(threadIdx.x & 31), warp = (int)(threadIdx.x >> 5);
+    const int sub = lane & (CL - 1), slot = lane / CL;
+    const int coil = sub * VC;
+    const bool coil_ok = coil < C;
+    const char *gb = reinterpret_cast<const char *>(grid + (coil_ok ? coil : 0));
+    const uint64_t rowbytes = (uint64_t)n0 * pitch;
+    const bool dense_pitch = pitch == (uint32_t)PITCH;
+    const int64_t s0 = ((int64_t)blockIdx.x * 8 + warp) * (int64_t)(SPW * iters);
+    for (int it = 0; it < iters; ++it) {
+        const int64_t rbase = s0 + (int64_t)it * SPW;
+        if (rbase >= m) break;                                       // warp-uniform
+        const int64_t r = rbase + slot;
+        float wx[kKbTaps], wy[kKbTaps], wz[kKbTaps];
+        int ix0 = 0, iy0 = 0, iz0 = 0, out = -1, nt = 0;
+        if (r < m) {
+            const float4 *p = reinterpret_cast<const float4 *>(rec + r);
+            const float4 a = __ldcs(p), b = __ldcs(p + 1), c = __ldcs(p + 2), d = __ldcs(p + 3), e = __ldcs(p + 4);
+            const int4 g = __ldcs(reinterpret_cast<const int4 *>(p + 5));
+            wx[0] = a.x; wx[1] = a.y; wx[2] = a.z; wx[3] = a.w; wx[4] = b.x; wx[5] = b.y;
+            wy[0] = b.z; wy[1] = b.w; wy[2] = c.x; wy[3] = c.y; wy[4] = c.z; wy[5] = c.w;
+            wz[0] = d.x; wz[1] = d.y; wz[2] = d.z; wz[3] = d.w; wz[4] = e.x; wz[5] = e.y;
+            ix0 = __float_as_int(e.z); iy0 = __float_as_int(e.w); iz0 = g.x; out = g.y; nt = g.z;
+        } else {
+#pragma unroll
+            for (int t = 0; t < kKbTaps; ++t) { wx[t] = 0.f; wy[t] = 0.f; wz[t] = 0.f; }
+        }
+        const int nxm = __reduce_max_sync(FULL, nt & 255), nym = __reduce_max_sync(FULL, (nt >> 8) & 255),
+                  nzm = __reduce_max_sync(FULL, (nt >> 16) & 255);
+        const bool sixth = nxm > kKbTaps - 1;
+        const bool dense = dense_pitch && __all_sync(FULL, ix0 + kKbTaps <= n0);
+        uint32_t xo[kKbTaps];
+        {
+            int j = ix0;
+#pragma unroll
+            for (int t = 0; t < kKbTaps; ++t) { xo[t] = (uint32_t)j * pitch; if (++j >= n0) j = 0; }
+        }
+        float ax[VC], ay[VC];
+#pragma unroll
+        for (int v = 0; v < VC; ++v) { ax[v] = 0.f; ay[v] = 0.f; }
+        int iz = iz0;
+        for (int k = 0; k < nzm; ++k) {
+            const float wk = wz[0];
+#pragma unroll
+            for (int t = 0; t < kKbTaps - 1; ++t) wz[t] = wz[t + 1];
+            wz[kKbTaps - 1] = 0.f;
+            const uint64_t zrow = (uint64_t)iz * (uint64_t)n1;
+            int iy = iy0;
+            if (dense) {
+#pragma unroll
+                for (int j = 0; j < kKbTaps; ++j) {
+                    if (j < nym) {                                   // warp-uniform
+                        kb_row<VC, true, PITCH>(gb + (zrow + (uint64_t)iy) * rowbytes, xo, wx, sixth, wk * wy[j], ax, ay);
+                        if (++iy >= n1) iy = 0;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < kKbTaps; ++j) {
+                    if (j < nym) {
+                        kb_row<VC, false, PITCH>(gb + (zrow + (uint64_t)iy) * rowbytes, xo, wx, sixth, wk * wy[j], ax, ay);
+                        if (++iy >= n1) iy = 0;
+                    }
+                }
+            }
+            if (++iz >= n2) iz = 0;
+        }
+        if (out >= 0 && coil_ok) {
+            c64 *yp = Y + (int64_t)out * ypitch + coil;
+            if (VC == 2) {
+                const c64 o0 = cmul(alpha, mk(ax[0], ay[0])), o1 = cmul(alpha, mk(ax[VC - 1], ay[VC - 1]));
+                __stcs(reinterpret_cast<float4 *>(yp), make_float4(o0.x, o0.y, o1.x, o1.y));
+            } else {
+                __stcs(yp, cmul(alpha, mk(ax[0], ay[0])));
+            }
+        }
+    }
+}
+
+template <int CL, int VC>
+static int launch_kb_gather(cudaStream_t s, int64_t m, int C, c64 alpha, const KbRecord *rec, const c64 *grid,
+                            int64_t xpitch, const int64_t n[3], c64 *Y, int64_t ypitch) {
+    constexpr int SPW = 32 / CL;
+    // ~32 samples per warp: long enough to amortise the launch of a CTA, short enough for >= 20 waves
+    int iters = 32 / SPW; if (iters < 1) iters = 1;
+    const int64_t per_cta = (int64_t)8 * SPW * iters;
+    const int64_t blocks = ceil_div(m, per_cta);
+    IB200_REQUIRE(blocks < (1LL << 31), "too many samples for one launch");
+    kb_gather_kernel<CL, VC><<<(unsigned)blocks, 256, 0, s>>>(m, C, alpha, rec, grid, (uint32_t)(xpitch * sizeof(c64)),
+                                                              (int)n[0], (int)n[1], (int)n[2], Y, ypitch, iters);
+    IB200_LAUNCH_CHECK();
+    return 0;
+}
+
+static int kb_pow2_ceil(int64_t v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+}  // namespace ib200
+
+using namespace ib200;
+
+extern "C" {
+
+int ib200_kb_record_bytes(void) { return (int)sizeof(KbRecord); }
+
+int ib200_kb_records(void *stream, int64_t m, const double *coord, const int64_t grid[3], double width,
+                     const double *table, int ntable, const float *rowweight, const float *f0, const float *f1,
+                     const float *f2, const int32_t *perm, void *records, int *host_flag) {
+    IB200_REQUIRE(m >= 0 && grid && host_flag, "bad arguments");
+    *host_flag = 0;
+    if (m == 0) return 0;
+    IB200_REQUIRE(coord && table && f0 && f1 && f2 && records, "null pointer");
+    IB200_REQUIRE(ntable >= 2, "table too short");
+    IB200_REQUIRE(width > 0, "kernel width must be positive");
+    IB200_REQUIRE(grid[0] > 0 && grid[1] > 0 && grid[2] > 0 && grid[0] * grid[1] * grid[2] < (1LL << 31),
+                  "grid must be positive and hold fewer than 2^31 points");
+    cudaStream_t s = as_stream(stream);
+    int *flag = nullptr;
+    IB200_TRY(cudaMalloc(&flag, sizeof(int)));
+    cudaMemsetAsync(flag, 0, sizeof(int), s);
+    kb_records_kernel<<<(unsigned)ceil_div(m, 128), 128, 0, s>>>(m, coord, (int)grid[0], (int)grid[1], (int)grid[2], width,
+                                                                table, ntable, rowweight, f0, f1, f2, perm,
+                                                                (KbRecord *)records, flag);
+    count_launch();
+    cudaMemcpyAsync(host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    cudaFree(flag);
+    IB200_TRY(e);
+    IB200_TRY(cudaGetLastError());
+    return 0;
+}
+
+int ib200_kb_gather(void *stream, int64_t m, int64_t ncols, float ar, float ai, const void *records,
+                    const void *grid_il, int64_t xpitch, const int64_t grid[3], void *Yil, int64_t ypitch) {
+    IB200_REQUIRE(m >= 0 && ncols >= 0 && grid, "bad arguments");
+    if (m == 0 || ncols == 0) return 0;
+    IB200_REQUIRE(records && grid_il && Yil, "null pointer");
+    IB200_REQUIRE(ncols <= 64, "separable gather serves at most 64 columns per call");
+    IB200_REQUIRE(xpitch >= ncols && ypitch >= ncols, "pitch smaller than the column count");
+    IB200_REQUIRE(grid[0] > 0 && grid[1] > 0 && grid[2] > 0, "bad grid");
+    IB200_REQUIRE(xpitch * (int64_t)sizeof(c64) * grid[0] < (1LL << 32), "grid row too long");
+    const c64 alpha = mk(ar, ai);
+    cudaStream_t s = as_stream(stream);
+    const bool vec2 = ncols % 2 == 0 && xpitch % 2 == 0 && ypitch % 2 == 0 && ((uintptr_t)grid_il % 16) == 0 &&
+                      ((uintptr_t)Yil % 16) == 0;
+    const int CL = kb_pow2_ceil(vec2 ? ncols / 2 : ncols);
+    IB200_REQUIRE(CL <= 32, "too many columns for one lane group");
+#define IB200_KB_CASE(cl)                                                                                            \
+    case cl:                                                                                                         \
+        return vec2 ? launch_kb_gather<cl, 2>(s, m, (int)ncols, alpha, (const KbRecord *)records, (const c64 *)grid_il, \
+                                              xpitch, grid, (c64 *)Yil, ypitch)                                      \
+                    : launch_kb_gather<cl, 1>(s, m, (int)ncols, alpha, (const KbRecord *)records, (const c64 *)grid_il, \
+                                              xpitch, grid, (c64 *)Yil, ypitch)
+    switch (CL) {
+        IB200_KB_CASE(1); IB200_KB_CASE(2); IB200_KB_CASE(4); IB200_KB_CASE(8); IB200_KB_CASE(16); IB200_KB_CASE(32);
+    }
+#undef IB200_KB_CASE
+    set_error("internal: no separable gather for CL=%d", CL);
+    return IB200_E_UNSUPPORTED;
+}
+
+}  // extern "C"

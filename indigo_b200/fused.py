@@ -37,9 +37,10 @@ class SenseDevice(object):
     # entries; one coil per lane for the long forward rows, two coils per lane for the short adjoint rows
     staged_fwd = -41
     staged_adj = -4
+    allow_separable = True     # forward gridding from 96-byte separable-weight records instead of stored entries
 
     def __init__(self, B, N, coord, maps, oversamp=2.0, weights=None, width=3, n=128):
-        from .sense import gridding_matrix_device, _fftc_mod
+        from .sense import gridding_matrix_device, _fftc_mod, kb_records_device
         from .host.noncart import rolloff3
 
         self.B = B
@@ -80,7 +81,7 @@ class SenseDevice(object):
         del colrank, work
         # real-weight packed entries (8 B instead of 12 B per stored entry, half the multiplies) when
         # the centring phase folded into G' is real, i.e. on every grid the fused path serves
-        self.real = False
+        self.real, self.kb = False, None
         if self.nnz and self.allow_real:
             pk = np.dtype('int64')                                     # 8-byte (int32 column, float32 weight) records
             g_pk = B.zero_array((self.nnz + 2,), pk, name='G.packed')  # +2: the staged kernel copies 16-byte granules
@@ -105,6 +106,13 @@ class SenseDevice(object):
                 lib.csr_permute_rows(s, self.M, self.nnz, self.G.rowPtrs.ptr, g_pk.ptr, rank8.ptr, nr8,
                                      self.g_ptr.ptr, self.g_pk.ptr, self.g_map.ptr)
                 del rank8, junk
+                # separable Kaiser-Bessel records in the same tile-sorted order: the forward gather then
+                # needs no stored entries at all (csrc/kbgrid.cu)
+                self.kb = None
+                if self.allow_separable:
+                    self.kb = kb_records_device(B, self.oN, coord, beta, weights, width, n, perm=self.g_map)
+                if self.kb is not None:
+                    self.g_pk = self.g_ptr = None
             del g_pk
         # rows of G'^H that are long enough to deserve a whole CTA (k-space centre of radial trajectories)
         cnt = ctypes.c_int()
@@ -132,7 +140,10 @@ class SenseDevice(object):
     def grid_to_samples(self, alpha=1.0):
         a = complex(alpha)
         G, lib, s = self.G, self.B._lib, self.B._stream
-        if self.real:
+        if self.real and self.kb is not None:
+            lib.kb_gather(s, self.M, self.C, a.real, a.imag, self.kb.ptr, self.grid.ptr, self.C,
+                          (ctypes.c_int64 * 3)(*self.oN), self.ksp.ptr, self.C)
+        elif self.real:
             lib.ccsrmm_ilr(s, self.M, self.on, self.C, self.nnz, a.real, a.imag, self.g_pk.ptr, self.g_ptr.ptr,
                            self.grid.ptr, self.C, self.ksp.ptr, self.C, self.g_map.ptr, self.staged_fwd, None, 0, 0)
         else:

@@ -152,6 +152,52 @@ def gridding_matrix_device(B, N, coord, oversamp=2.0, weights=None, width=3, n=1
     return Gd, oN, omin, beta
 
 
+def _fftc_axis_factors(oN):
+    """Per-axis factors of mod*scale (backend.py:349-364): mod = prod_d exp(2 pi i (i_d - c_d/2) c_d/n_d).
+    Returns three float32 arrays (the scale folded into the last) when every factor is real to
+    rounding, else None."""
+    out = []
+    for d in range(3):
+        c = oN[d] // 2
+        m = np.exp(1j * 2.0 * np.pi * ((np.arange(oN[d]) - c / 2.0) * (c / oN[d])))
+        if np.abs(m.imag).max() > 1e-6:
+            return None
+        out.append(m.real.astype(np.float32))
+    scl = np.float32(np.complex64(np.complex128(1.0) / np.sqrt(int(np.prod(oN)))).real)
+    out[2] = (out[2] * scl).astype(np.float32)
+    return out
+
+
+def kb_records_device(B, oN, coord, beta, weights=None, width=3, n=128, perm=None):
+    """Separable-weight records of G' = interp*mod*scale (ib200_kb_records, csrc/kbgrid.cu): 96 bytes per
+    sample instead of a stored row.  perm (device int32, optional): record r describes sample perm[r].
+    Returns the device array of records, or None when this grid / kernel width is not served
+    (complex centring phase, more than 6 taps per axis)."""
+    import ctypes
+    from scipy.signal.windows import kaiser
+
+    fac = _fftc_axis_factors(oN)
+    if fac is None or 2 * width > 6:
+        return None
+    lib, s = B._lib, B._stream
+    table = np.ascontiguousarray(kaiser(2 * n + 1, beta)[n:], dtype=np.float64)
+    c3 = np.asfortranarray(np.asarray(coord).reshape((3, -1), order='F').astype(np.float64))
+    m = c3.shape[1]
+    coord_d, table_d = B.copy_array(c3), B.copy_array(table)
+    f_d = [B.copy_array(np.ascontiguousarray(f)) for f in fac]
+    w_d = None
+    if weights is not None:
+        w_d = B.copy_array(np.ascontiguousarray(np.asarray(weights, dtype=np.float32).reshape(-1)))
+    nb = int(lib.kb_record_bytes())
+    rec = B.empty_array((max(m, 1) * nb // 8,), np.dtype('int64'), name='G.records')
+    flag = ctypes.c_int()
+    grid = (ctypes.c_int64 * 3)(*oN)
+    lib.kb_records(s, m, coord_d.ptr, grid, float(width), table_d.ptr, int(table.size),
+                   w_d.ptr if w_d is not None else None, f_d[0].ptr, f_d[1].ptr, f_d[2].ptr,
+                   perm.ptr if perm is not None else None, rec.ptr, ctypes.byref(flag))
+    return rec if flag.value == 0 else None
+
+
 def sense_operator_device(B, N, coord, maps, oversamp=2.0, weights=None, width=3, n=128):
     """Same operator, same -O3 tree shape and the same six backend calls per A^H A as
     sense_operator(), but G' and P^H are built on the GPU (ib200_kb_* / ib200_sense_ph_*)

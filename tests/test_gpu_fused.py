@@ -43,14 +43,17 @@ def _setup(N, C, traj, weighted, seed=0):
     return rs, coord, maps, w
 
 
-@pytest.mark.parametrize("real", [True, False], ids=["real-packed", "complex"])
+@pytest.mark.parametrize("mode", ["separable", "real-packed", "complex"])
 @pytest.mark.parametrize("N,C,traj,weighted", CASES)
-def test_fused_against_oracle(B, N, C, traj, weighted, real, monkeypatch):
+def test_fused_against_oracle(B, N, C, traj, weighted, mode, monkeypatch):
     from indigo_b200 import fused
+    real = mode != "complex"
     monkeypatch.setattr(fused.SenseDevice, "allow_real", real)
+    monkeypatch.setattr(fused.SenseDevice, "allow_separable", mode == "separable")
     rs, coord, maps, w = _setup(N, C, traj, weighted)
     A = sense_operator_fused(B, N, coord, maps, 2.0, weights=w)
     assert A._dev.real == real
+    assert (A._dev.kb is not None) == (mode == "separable")
     ref = osense.SenseOperator(N, coord, maps, 2.0, weights=w)
     nvox = int(np.prod(N))
     x = synth.rand64c(rs, nvox, 1)
