@@ -18,6 +18,7 @@
 // the CPU emulation harness used by the GPU-less tests).
 #include "fft_plan.hpp"
 #include "fft_il.cuh"
+#include "fft_pk.cuh"
 
 #include <cstdlib>
 #include <new>
@@ -160,11 +161,149 @@ static int try_il_pass(cudaStream_t s, const IlPassArgs &a, int n, const FftStag
     return 0;
 }
 
+// ---- packed two-lines-per-thread variants (fft_pk.cuh): 256 threads, split-plane tiles ----------------
+static const int kPkThreads = 256;
+static bool pk_enabled() { static const bool on = getenv("IB200_FFT_NOPK") == nullptr; return on; }
+
+template <int N, int R0, int R1, int R2, bool SI, bool SO>
+__global__ void __launch_bounds__(kPkThreads, 2) fft_pk_pass_kernel(const IlPassArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    fft_pk_pass_body<N, R0, R1, R2, SI, SO, kPkThreads>(a, reinterpret_cast<float *>(smem_raw), (int64_t)blockIdx.x, (int)threadIdx.x,
+                                            (int)blockDim.x);
+}
+
+template <int N, int R0, int R1, int R2, bool SI, bool SO>
+static int launch_pk_pass(cudaStream_t s, const IlPassArgs &a) {
+    static bool attr_done[64] = {false};
+    const size_t smem = pk_smem_floats(N, R2 > 1, false) * sizeof(float);
+    if ((int64_t)smem > smem_optin()) return -100;                  // caller falls back to the one-line kernels
+    int dev = 0;
+    IB200_TRY(cudaGetDevice(&dev));
+    if (!attr_done[dev & 63]) {
+        IB200_TRY(cudaFuncSetAttribute(fft_pk_pass_kernel<N, R0, R1, R2, SI, SO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[dev & 63] = true;
+    }
+    const int64_t blocks = (a.inner / kSpecL) * a.outer;
+    IB200_REQUIRE(blocks < (1LL << 31), "fft: too many tiles for one launch");
+    fft_pk_pass_kernel<N, R0, R1, R2, SI, SO><<<(unsigned)blocks, kPkThreads, smem, s>>>(a);
+    IB200_LAUNCH_CHECK();
+    return 0;
+}
+
+// persistent prefetching form (fft_pk.cuh): one CTA pair per SM walks the tiles
+template <int N, int R0, int R1, int R2, bool SI, bool SO>
+__global__ void __launch_bounds__(kPkThreads, 2) fft_pkp_pass_kernel(const IlPassArgs a, int64_t ntiles) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *bufA = reinterpret_cast<float *>(smem_raw);
+    c64 *raw = reinterpret_cast<c64 *>(bufA + pk_buf_floats(N));
+    int64_t tile = blockIdx.x;
+    if (tile >= ntiles) return;
+    pkp_prefetch(a, tile, raw, (int)threadIdx.x, kPkThreads);
+    for (; tile < ntiles; tile += gridDim.x) {
+        const int64_t next = tile + gridDim.x < ntiles ? tile + gridDim.x : -1;
+        pkp_wait();
+        __syncthreads();                                             // raw[] of this tile visible; bufA of the last tile consumed
+        fft_pkp_tile_body<N, R0, R1, R2, SI, SO, kPkThreads>(a, tile, next, bufA, raw, (int)threadIdx.x, kPkThreads);
+    }
+}
+
+template <int N, int R0, int R1, int R2, bool SI, bool SO>
+static int launch_pkp_pass(cudaStream_t s, const IlPassArgs &a) {
+    static bool attr_done[64] = {false};
+    const size_t smem = pk_buf_floats(N) * sizeof(float) + (size_t)N * kSpecL * sizeof(c64);
+    if ((int64_t)smem > smem_optin()) return -100;
+    int dev = 0;
+    IB200_TRY(cudaGetDevice(&dev));
+    if (!attr_done[dev & 63]) {
+        IB200_TRY(cudaFuncSetAttribute(fft_pkp_pass_kernel<N, R0, R1, R2, SI, SO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[dev & 63] = true;
+    }
+    const int64_t ntiles = (a.inner / kSpecL) * a.outer;
+    static const int per_sm = getenv("IB200_FFT_PKP_CTAS") ? atoi(getenv("IB200_FFT_PKP_CTAS")) : 2;
+    int64_t blocks = (int64_t)sm_count() * per_sm;
+    if (blocks > ntiles) blocks = ntiles;
+    fft_pkp_pass_kernel<N, R0, R1, R2, SI, SO><<<(unsigned)blocks, kPkThreads, smem, s>>>(a, ntiles);
+    IB200_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int N, int R0, int R1, int R2, bool SI, bool SO>
+static int launch_pk_or_pkp(cudaStream_t s, const IlPassArgs &a) {
+    static const bool persistent = getenv("IB200_FFT_NOPKP") == nullptr;
+    if (persistent && pkp_mid_pairs(N, R1, R2, kPkThreads) <= 16) {
+        const int rc = launch_pkp_pass<N, R0, R1, R2, SI, SO>(s, a);
+        if (rc != -100) return rc;
+    }
+    return launch_pk_pass<N, R0, R1, R2, SI, SO>(s, a);
+}
+
+// returns 1 when launched, 0 when not applicable, else an error code (+1000 when positive)
+static int try_pk_pass(cudaStream_t s, const IlPassArgs &a, int n, const FftStages &st, bool swap_in, bool swap_out) {
+    if (!pk_enabled() || (a.outer_stride & 1) || ((uintptr_t)a.x & 15)) return 0;
+    FftKernelArgs k;
+    k.n = n; k.st = st;
+#define IB200_PK_PASS(nn, r0, r1, r2)                                                            \
+    if (fft_spec_matches(k, nn, r0, r1, r2)) {                                                   \
+        int rc;                                                                                  \
+        if (swap_in)       rc = launch_pk_or_pkp<nn, r0, r1, r2, true, false>(s, a);             \
+        else if (swap_out) rc = launch_pk_or_pkp<nn, r0, r1, r2, false, true>(s, a);             \
+        else               rc = launch_pk_or_pkp<nn, r0, r1, r2, false, false>(s, a);            \
+        if (rc == -100) return 0;                                                                \
+        return rc == 0 ? 1 : (rc > 0 ? rc + 1000 : rc);                                          \
+    }
+    IB200_FFT_SPEC_LIST(IB200_PK_PASS)
+#undef IB200_PK_PASS
+    return 0;
+}
+
+template <int N, int R0, int R1, int R2>
+__global__ void __launch_bounds__(kPkThreads, 2) sense_expand_pk_kernel(const SenseFftArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    sense_expand_pk_body<N, R0, R1, R2, kPkThreads>(a, reinterpret_cast<float *>(smem_raw), (int64_t)blockIdx.x, (int)threadIdx.x,
+                                        (int)blockDim.x);
+}
+
+template <int N, int R0, int R1, int R2>
+__global__ void __launch_bounds__(kPkThreads, 2) sense_combine_pk_kernel(const SenseFftArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *buf = reinterpret_cast<float *>(smem_raw);
+    sense_combine_pk_body<N, R0, R1, R2, kPkThreads>(a, buf, reinterpret_cast<c64 *>(buf + pk_smem_floats(N, R2 > 1, true)),
+                                         (int64_t)blockIdx.x, (int)threadIdx.x, (int)blockDim.x);
+}
+
+// returns 0 when launched, -100 when the packed kernels do not apply
+template <int N, int R0, int R1, int R2>
+static int launch_sense_x_pk(cudaStream_t s, bool combine, const SenseFftArgs &a) {
+    static bool attr_done[2][64] = {{false}};
+    if (!pk_enabled() || (a.C & 1)) return -100;
+    if (((uintptr_t)a.grid & 15) || ((uintptr_t)a.pf & 15)) return -100;
+    const size_t smem = combine ? pk_smem_floats(N, R2 > 1, true) * sizeof(float) + (size_t)a.N0 * sense_x_tile(a.C).YY * sizeof(c64)
+                                : pk_smem_floats(N, R2 > 1, false) * sizeof(float);
+    if ((int64_t)smem > smem_optin()) return -100;
+    int dev = 0;
+    IB200_TRY(cudaGetDevice(&dev));
+    if (!attr_done[combine ? 1 : 0][dev & 63]) {
+        if (combine) IB200_TRY(cudaFuncSetAttribute(sense_combine_pk_kernel<N, R0, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin()));
+        else         IB200_TRY(cudaFuncSetAttribute(sense_expand_pk_kernel<N, R0, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin()));
+        attr_done[combine ? 1 : 0][dev & 63] = true;
+    }
+    const int64_t blocks = sense_x_blocks(a.N1, a.N2, a.C);
+    IB200_REQUIRE(blocks < (1LL << 31), "sense x pass: too many rows for one launch");
+    if (combine) sense_combine_pk_kernel<N, R0, R1, R2><<<(unsigned)blocks, kPkThreads, smem, s>>>(a);
+    else         sense_expand_pk_kernel<N, R0, R1, R2><<<(unsigned)blocks, kPkThreads, smem, s>>>(a);
+    IB200_LAUNCH_CHECK();
+    return 0;
+}
+
 static int run_sense_x(cudaStream_t s, bool combine, const SenseFftArgs &a, const FftStages &st) {
     FftKernelArgs k;
     k.n = a.n0; k.st = st;
-#define IB200_SENSE_X(n, r0, r1, r2) \
-    if (fft_spec_matches(k, n, r0, r1, r2)) return launch_sense_x<n, r0, r1, r2>(s, combine, a);
+#define IB200_SENSE_X(n, r0, r1, r2)                                       \
+    if (fft_spec_matches(k, n, r0, r1, r2)) {                              \
+        const int rc = launch_sense_x_pk<n, r0, r1, r2>(s, combine, a);    \
+        if (rc != -100) return rc;                                         \
+        return launch_sense_x<n, r0, r1, r2>(s, combine, a);               \
+    }
     IB200_FFT_SPEC_LIST(IB200_SENSE_X)
 #undef IB200_SENSE_X
     set_error("fused SENSE passes need a grid extent with a specialised FFT (got %d)", a.n0);
@@ -307,7 +446,10 @@ static int sense_strided_pass(ib200_sense_plan_s *p, cudaStream_t s, c64 *grid, 
         IlPassArgs a;
         a.x = base; a.tw = ax.tw_dev; a.inner = k.inner; a.outer = k.outer; a.outer_stride = k.outer_stride;
         a.pstride = (unsigned)k.inner; a.in0 = k.in0; a.in1 = k.in1; a.out0 = k.out0; a.out1 = k.out1;
-        const int r = try_il_pass(s, a, ax.n, ax.st, k.swap_in != 0, k.swap_out != 0);
+        int r = try_pk_pass(s, a, ax.n, ax.st, k.swap_in != 0, k.swap_out != 0);
+        if (r == 1) return 0;
+        if (r != 0) return r > 1000 ? r - 1000 : r;
+        r = try_il_pass(s, a, ax.n, ax.st, k.swap_in != 0, k.swap_out != 0);
         if (r == 1) return 0;
         if (r != 0) return r > 1000 ? r - 1000 : r;
     }

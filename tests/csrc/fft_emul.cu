@@ -5,7 +5,9 @@
 // The product never links this file.
 #include "../../indigo_b200/csrc/fft_plan.hpp"
 #include "../../indigo_b200/csrc/fft_il.cuh"
+#include "../../indigo_b200/csrc/fft_pk.cuh"
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -22,6 +24,8 @@ int64_t smem_optin() { return 232448; }
 using namespace ib200;
 
 extern "C" const char *emul_last_error() { return g_err; }
+static int g_pk_used = 0;
+extern "C" int emul_pk_used() { const int v = g_pk_used; g_pk_used = 0; return v; }
 
 extern "C" int emul_fft(int ndim, const int64_t *dims, int64_t batch, float *y, const float *x, int direction,
                         const float *din, int conj_in, const float *dout, int conj_out, int *tile_L_out) {
@@ -87,6 +91,32 @@ static int emul_strided(const AxisPlan &ax, c64 *base, int64_t inner, int64_t ou
         IlPassArgs a;
         a.x = base; a.tw = ax.tw_dev; a.inner = inner; a.outer = outer; a.outer_stride = outer_stride;
         a.pstride = (unsigned)inner; a.in0 = in0; a.in1 = in1; a.out0 = out0; a.out1 = out1;
+        if (getenv("IB200_FFT_NOPK") == nullptr && (outer_stride & 1) == 0) {   // same choice as try_pk_pass (fft.cu)
+#define EMUL_PK(n, r0, r1, r2)                                                                     \
+            if (!done && fft_spec_matches(k, n, r0, r1, r2)) {                                     \
+                done = true; ++g_pk_used;                                                          \
+                std::vector<float> sp(2 * pk_buf_floats(n) + 4);                                   \
+                const int64_t nb = (inner / kSpecL) * outer;                                       \
+                const bool pkp = getenv("IB200_FFT_NOPKP") == nullptr && pkp_mid_pairs(n, r1, r2, 256) <= 16; \
+                std::vector<c64> raw((size_t)n * kSpecL + 2);                                      \
+                for (int64_t b = 0; b < nb; ++b) {                                                 \
+                    if (pkp) {      /* persistent form: prefetch of tile b, then the tile body (next = none) */ \
+                        for (auto &v : raw) v = mk(NAN, NAN);                                      \
+                        pkp_prefetch(a, b, raw.data(), 0, 1);                                      \
+                        if (swap_in)       fft_pkp_tile_body<n, r0, r1, r2, true, false, 0>(a, b, -1, sp.data(), raw.data(), 0, 1); \
+                        else if (swap_out) fft_pkp_tile_body<n, r0, r1, r2, false, true, 0>(a, b, -1, sp.data(), raw.data(), 0, 1); \
+                        else               fft_pkp_tile_body<n, r0, r1, r2, false, false, 0>(a, b, -1, sp.data(), raw.data(), 0, 1); \
+                        continue;                                                                  \
+                    }                                                                              \
+                    if (swap_in)       fft_pk_pass_body<n, r0, r1, r2, true, false, 0>(a, sp.data(), b, 0, 1);  \
+                    else if (swap_out) fft_pk_pass_body<n, r0, r1, r2, false, true, 0>(a, sp.data(), b, 0, 1);  \
+                    else               fft_pk_pass_body<n, r0, r1, r2, false, false, 0>(a, sp.data(), b, 0, 1); \
+                }                                                                                  \
+            }
+            IB200_FFT_SPEC_LIST(EMUL_PK)
+#undef EMUL_PK
+            if (done) return 0;
+        }
 #define EMUL_IL(n, r0, r1, r2)                                                                     \
         if (!done && fft_spec_matches(k, n, r0, r1, r2)) {                                         \
             done = true;                                                                           \
@@ -131,7 +161,16 @@ extern "C" int emul_sense(const int64_t *N, const int64_t *oN, int64_t C, int wh
     const int64_t sy = oN[0] * C, sz = sy * oN[1];
     FftKernelArgs k0; k0.n = a.n0; k0.st = pl.ax[0].st;
     bool done = false;
+    const bool pk = getenv("IB200_FFT_NOPK") == nullptr && (C % 2) == 0;          // same choice as launch_sense_x_pk
     if (which == 0) {            // expand + forward FFT
+#define EMUL_XP(n, r0, r1, r2)                                                                     \
+        if (pk && !done && fft_spec_matches(k0, n, r0, r1, r2)) {                                  \
+            done = true; ++g_pk_used;                                                              \
+            std::vector<float> sp(2 * pk_buf_floats(n) + 4);                                       \
+            for (int64_t b = 0; b < sense_x_blocks((int)N[1], (int)N[2], (int)C); ++b) sense_expand_pk_body<n, r0, r1, r2, 0>(a, sp.data(), b, 0, 1); \
+        }
+        IB200_FFT_SPEC_LIST(EMUL_XP)
+#undef EMUL_XP
 #define EMUL_X(n, r0, r1, r2)                                                                      \
         if (!done && fft_spec_matches(k0, n, r0, r1, r2)) {                                        \
             done = true;                                                                           \
@@ -150,6 +189,15 @@ extern "C" int emul_sense(const int64_t *N, const int64_t *oN, int64_t C, int wh
     if (rc) return rc;
     rc = emul_strided(pl.ax[1], (c64 *)grid + off[2] * sz, sy, N[2], sz, 0, (int)oN[1], (int)off[1], (int)(off[1] + N[1]), 0, 0);
     if (rc) return rc;
+#define EMUL_CP(n, r0, r1, r2)                                                                     \
+    if (pk && !done && fft_spec_matches(k0, n, r0, r1, r2)) {                                      \
+        done = true; ++g_pk_used;                                                                  \
+        std::vector<float> sp(2 * pk_buf_floats(n) + 4);                                           \
+        std::vector<c64> acc((size_t)N[0] * kSpecL + 1);                                           \
+        for (int64_t b = 0; b < sense_x_blocks((int)N[1], (int)N[2], (int)C); ++b) sense_combine_pk_body<n, r0, r1, r2, 0>(a, sp.data(), acc.data(), b, 0, 1); \
+    }
+    IB200_FFT_SPEC_LIST(EMUL_CP)
+#undef EMUL_CP
 #define EMUL_C(n, r0, r1, r2)                                                                      \
     if (!done && fft_spec_matches(k0, n, r0, r1, r2)) {                                            \
         done = true;                                                                               \

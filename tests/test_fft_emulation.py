@@ -79,9 +79,14 @@ def emul_sense():
     def run(which, N, oN, C, grid, img, pf, alpha=1.0, beta=0.0):
         a, b = complex(alpha), complex(beta)
         n, on = i64(N), i64(oN)
+        lib.emul_pk_used()
         rc = lib.emul_sense(p(n), p(on), ctypes.c_int64(C), which, p(grid), p(img), p(pf),
                             ctypes.c_float(a.real), ctypes.c_float(a.imag), ctypes.c_float(b.real), ctypes.c_float(b.imag))
         assert rc == 0
+        # the packed two-lines-per-thread bodies (fft_pk.cuh) serve all three passes when the coil count is
+        # even, the strided passes alone otherwise (unless disabled through IB200_FFT_NOPK)
+        if os.environ.get("IB200_FFT_NOPK") is None:
+            assert lib.emul_pk_used() == (3 if C % 2 == 0 else 2)
     return run
 
 
@@ -92,7 +97,12 @@ def _crand(rs, *shape):
 @pytest.mark.parametrize("N,oN,C", [((16, 16, 16), (32, 32, 32), 16), ((16, 26, 16), (32, 52, 32), 4),
                                     ((13, 20, 16), (32, 32, 52), 20), ((32, 16, 26), (64, 32, 52), 3),
                                     ((16, 13, 8), (32, 32, 32), 2), ((16, 15, 4), (32, 32, 32), 8),
-                                    ((16, 16, 5), (32, 32, 32), 1)])
+                                    ((16, 16, 5), (32, 32, 32), 1),
+                                    # every radix of the specialised passes: (16,8) (3,8,8) (13,16) (5,8,8) (7,8,8) (16,16) (13,8,4)
+                                    ((64, 16, 16), (128, 32, 32), 2), ((96, 16, 8), (192, 32, 32), 2),
+                                    ((16, 104, 8), (32, 208, 32), 2), ((16, 8, 160), (32, 32, 320), 2),
+                                    ((224, 16, 8), (448, 32, 32), 2), ((16, 128, 8), (32, 256, 32), 4),
+                                    ((8, 16, 208), (32, 32, 416), 6)])
 def test_fused_sense_expand_and_combine(emul_sense, N, oN, C):
     """grid[z][y][x][c] = FFT3(zpad(pf*img)) and img = alpha*sum_c conj(pf)*crop(IFFT3_unscaled(grid)) + beta*img,
     against numpy on the same data (zero-pad placement of Backend.Zpad 'center', backend.py:371-387)."""
