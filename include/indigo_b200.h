@@ -169,6 +169,19 @@ int ib200_kb_records(void *stream, int64_t m, const double *coord, const int64_t
                      const float *f2, const int32_t *perm, void *records, int *host_flag);
 int ib200_kb_gather(void *stream, int64_t m, int64_t ncols, float alpha_re, float alpha_im, const void *records,
                     const void *grid_il, int64_t xpitch, const int64_t grid[3], void *Yil, int64_t ypitch);
+/* k-space support windows of a trajectory (fused SENSE recipe only).  Given the stored adjoint of the
+ * gridding matrix in tile-major row order (rowptr[kp+1], rowmap[kp] from ib200_grid_tile_rank) the
+ * grid columns are grouped into blocks of block[0] x block[1] points; for each block the hull [lo, hi)
+ * along z of the grid points that receive at least one sample is computed, rounded outwards to
+ * multiples of block[2].  win[2*(y*n0+x)], win[2*(y*n0+x)+1] receive the interval of column (x, y)
+ * ((0,0) when empty); rowmap_out is rowmap with every row outside its column's interval set to -1, so
+ * that the adjoint gather stores nothing there.  *host_inside = grid points inside the windows.
+ * Grid points outside are never read by the forward gridding and are exactly zero after the
+ * adjoint gridding, so ib200_sense_plan_set_support lets the last forward FFT pass skip writing them
+ * and the first inverse pass skip reading them (results are unchanged).  Synchronises. */
+int ib200_grid_support_windows(void *stream, const int64_t grid[3], int64_t kp, const int32_t *rowptr,
+                               const int32_t *rowmap, const int64_t block[3], int32_t *win, int32_t *rowmap_out,
+                               int64_t *host_inside);
 /* The inspector of _customcpu.c:179-215 on the device: out = {rows with >=1
  * entry, columns with >=1 entry, exwrite flag, max entries in one column}.
  * `work` is k int32 of device scratch.  Synchronises `stream`. */
@@ -240,6 +253,11 @@ int ib200_fft_exec_diag(ib200_fft_plan plan, void *stream, void *y, const void *
 typedef struct ib200_sense_plan_s *ib200_sense_plan;
 int ib200_sense_plan_create(ib200_sense_plan *plan, const int64_t N[3], const int64_t oN[3], int64_t ncoils);
 int ib200_sense_plan_destroy(ib200_sense_plan plan);
+/* win (device, 2 * oN[0]*oN[1] int32, see ib200_grid_support_windows; NULL disables) must stay valid
+ * while the plan is used; block_x is the block extent along x the windows were built with (a tile of
+ * 16 interleaved lines must not straddle two blocks: needs block_x*ncoils % 16 == 0 or ncoils % 16 == 0).
+ * Returns IB200_E_UNSUPPORTED when the geometry does not allow per-tile windows. */
+int ib200_sense_plan_set_support(ib200_sense_plan plan, const int32_t *win, int block_x);
 int ib200_sense_expand_fft(ib200_sense_plan plan, void *stream, void *grid_il, const void *img, const void *pf);
 int ib200_sense_ifft_combine(ib200_sense_plan plan, void *stream, void *img_out, void *grid_il, const void *pf,
                              float alpha_re, float alpha_im, float beta_re, float beta_im);

@@ -196,14 +196,16 @@ __global__ void __launch_bounds__(kPkThreads, 2) fft_pkp_pass_kernel(const IlPas
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *bufA = reinterpret_cast<float *>(smem_raw);
     c64 *raw = reinterpret_cast<c64 *>(bufA + pk_buf_floats(N));
-    int64_t tile = blockIdx.x;
-    if (tile >= ntiles) return;
-    pkp_prefetch(a, tile, raw, (int)threadIdx.x, kPkThreads);
-    for (; tile < ntiles; tile += gridDim.x) {
-        const int64_t next = tile + gridDim.x < ntiles ? tile + gridDim.x : -1;
+    const int tid = (int)threadIdx.x;
+    int64_t tile = pkp_next_active(a, blockIdx.x, gridDim.x, ntiles, tid, kPkThreads);
+    if (tile < 0) return;
+    pkp_prefetch(a, tile, raw, tid, kPkThreads);
+    while (tile >= 0) {
+        const int64_t next = pkp_next_active(a, tile + gridDim.x, gridDim.x, ntiles, tid, kPkThreads);
         pkp_wait();
         __syncthreads();                                             // raw[] of this tile visible; bufA of the last tile consumed
-        fft_pkp_tile_body<N, R0, R1, R2, SI, SO, kPkThreads>(a, tile, next, bufA, raw, (int)threadIdx.x, kPkThreads);
+        fft_pkp_tile_body<N, R0, R1, R2, SI, SO, kPkThreads>(a, tile, next, bufA, raw, tid, kPkThreads);
+        tile = next;
     }
 }
 
@@ -415,7 +417,26 @@ struct ib200_sense_plan_s {
     ib200_fft_plan fft;
     int64_t N[3], oN[3], off[3];
     int64_t C;
+    const int32_t *win = nullptr;          // k-space support windows of the z passes (ib200_sense_plan_set_support)
 };
+
+// does the z pass of this plan run on the persistent packed kernel (the only one that honours windows)?
+static bool sense_z_pass_is_persistent(const ib200_sense_plan_s *p) {
+    if (!pk_enabled() || getenv("IB200_FFT_NOPKP") || getenv("IB200_FFT_IL_GENERIC")) return false;
+    const AxisPlan &ax = p->fft->d.ax[2];
+    const int64_t sz = p->oN[0] * p->C * p->oN[1];
+    if (sz % kSpecL || sz >= (1LL << 32) || ((sz * p->oN[2]) & 1)) return false;
+    FftKernelArgs k;
+    k.n = ax.n; k.st = ax.st;
+    bool ok = false;
+#define IB200_PKP_OK(n, r0, r1, r2)                                                                         \
+    if (fft_spec_matches(k, n, r0, r1, r2))                                                                 \
+        ok = pkp_mid_pairs(n, r1, r2, kPkThreads) <= 16 &&                                                  \
+             (int64_t)(pk_buf_floats(n) * sizeof(float) + (size_t)n * kSpecL * sizeof(c64)) <= smem_optin();
+    IB200_FFT_SPEC_LIST(IB200_PKP_OK)
+#undef IB200_PKP_OK
+    return ok;
+}
 
 static int sense_strided_pass(ib200_sense_plan_s *p, cudaStream_t s, c64 *grid, int axis, bool inverse, bool first,
                               bool last) {
@@ -446,8 +467,10 @@ static int sense_strided_pass(ib200_sense_plan_s *p, cudaStream_t s, c64 *grid, 
         IlPassArgs a;
         a.x = base; a.tw = ax.tw_dev; a.inner = k.inner; a.outer = k.outer; a.outer_stride = k.outer_stride;
         a.pstride = (unsigned)k.inner; a.in0 = k.in0; a.in1 = k.in1; a.out0 = k.out0; a.out1 = k.out1;
+        if (axis == 2 && p->win) { a.win = p->win; a.win_mode = inverse ? 2 : 1; a.win_div = (int)p->C; }
         int r = try_pk_pass(s, a, ax.n, ax.st, k.swap_in != 0, k.swap_out != 0);
         if (r == 1) return 0;
+        if (axis == 2 && p->win && r == 0) { set_error("support windows set but the persistent z pass is unavailable"); return IB200_E_UNSUPPORTED; }
         if (r != 0) return r > 1000 ? r - 1000 : r;
         r = try_il_pass(s, a, ax.n, ax.st, k.swap_in != 0, k.swap_out != 0);
         if (r == 1) return 0;
@@ -484,6 +507,22 @@ int ib200_sense_plan_create(ib200_sense_plan *plan, const int64_t N[3], const in
     IB200_REQUIRE(oN[0] * ncoils >= kSpecL, "grid row too short");
     p->C = ncoils;
     *plan = p;
+    return 0;
+}
+
+int ib200_sense_plan_set_support(ib200_sense_plan plan, const int32_t *win, int block_x) {
+    IB200_REQUIRE(plan, "null plan");
+    if (!win) { plan->win = nullptr; return 0; }
+    IB200_REQUIRE(block_x >= 1, "bad block extent");
+    // all 16 lines of a tile must belong to grid points of one block
+    const int64_t C = plan->C;
+    bool ok = (C % kSpecL == 0) || (kSpecL % C == 0 && (block_x * C) % kSpecL == 0 && plan->oN[0] % block_x == 0);
+    if ((uintptr_t)win & 7) ok = false;
+    if (!ok || !sense_z_pass_is_persistent(plan)) {
+        set_error("support windows need the persistent packed z pass and tiles that do not straddle blocks");
+        return IB200_E_UNSUPPORTED;
+    }
+    plan->win = win;
     return 0;
 }
 

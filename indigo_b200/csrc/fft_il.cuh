@@ -169,6 +169,13 @@ struct IlPassArgs {
     int64_t inner, outer, outer_stride;
     unsigned pstride;
     int in0, in1, out0, out1;
+    // optional per-tile windows (k-space support of the trajectory, fft_pk.cuh): win[2*p], win[2*p+1] =
+    // [lo, hi) along the transformed axis for the grid point p = (first line of the tile) / win_div.
+    // win_mode 1: output window (forward pass; tiles with an empty window are skipped altogether);
+    // win_mode 2: input window (inverse pass; tiles with an empty window store zeros).  Persistent
+    // packed kernels only.
+    const int32_t *win = nullptr;
+    int win_mode = 0, win_div = 1;
 };
 
 template <int N, int R0, int R1, int R2, bool SWAP_IN, bool SWAP_OUT>

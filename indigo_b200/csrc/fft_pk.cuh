@@ -328,11 +328,25 @@ IB_HD const c64 *pkp_tile_base(const IlPassArgs &a, int64_t tile) {
 }
 
 // stream the input window of `tile` into raw[] (16-byte chunks, 8 per position)
+// window of a tile along the transformed axis: input window when `input`, else output window
+IB_HD void pkp_tile_window(const IlPassArgs &a, int64_t tile, bool input, int &lo, int &hi) {
+    lo = input ? a.in0 : a.out0; hi = input ? a.in1 : a.out1;
+    if (a.win && a.win_mode == (input ? 2 : 1)) {
+        const int64_t tiles = a.inner / kSpecL;
+        const int64_t p = ((tile % tiles) * kSpecL) / a.win_div;
+        const int wl = a.win[2 * p], wh = a.win[2 * p + 1];
+        lo = wl > lo ? wl : lo; hi = wh < hi ? wh : hi;
+        if (hi < lo) hi = lo;
+    }
+}
+
 IB_HD void pkp_prefetch(const IlPassArgs &a, int64_t tile, c64 *raw, int tid, int nt) {
     const c64 *g = pkp_tile_base(a, tile);
-    const int chunks = (a.in1 - a.in0) * kPkPairs;
+    int in0, in1;
+    pkp_tile_window(a, tile, true, in0, in1);
+    const int chunks = (in1 - in0) * kPkPairs;
     for (int i = tid; i < chunks; i += nt) {
-        const int pos = a.in0 + (i >> 3), ch = i & 7;
+        const int pos = in0 + (i >> 3), ch = i & 7;
         const c64 *src = g + (uint64_t)(unsigned)pos * a.pstride + 2 * ch;
         c64 *dst = raw + pos * kSpecL + 2 * ch;
 #ifdef __CUDA_ARCH__
@@ -412,6 +426,34 @@ IB_HD void pk_stage_inplace(const CTX &c, float *buf, int tid, int nt) {
 #endif
 }
 
+// Tiles the window mechanism lets a pass skip: forward passes skip tiles whose output window is empty;
+// inverse passes replace tiles whose input window is empty by zeros in the output window.  Returns
+// true when `tile` needs the transform.
+IB_HD bool pkp_tile_active(const IlPassArgs &a, int64_t tile) {
+    if (!a.win || a.win_mode == 0) return true;
+    int lo, hi;
+    pkp_tile_window(a, tile, a.win_mode == 2, lo, hi);
+    return hi > lo;
+}
+IB_HD void pkp_tile_zero_fill(const IlPassArgs &a, int64_t tile, int tid, int nt) {
+    c64 *g = const_cast<c64 *>(pkp_tile_base(a, tile));
+    const int chunks = (a.out1 - a.out0) * kPkPairs;
+    for (int i = tid; i < chunks; i += nt) {
+        const int pos = a.out0 + (i >> 3), ch = i & 7;
+        c64 *dst = g + (uint64_t)(unsigned)pos * a.pstride + 2 * ch;
+        dst[0] = h_mk(0.f, 0.f); dst[1] = h_mk(0.f, 0.f);
+    }
+}
+// first tile >= t (stride `step`) that needs the transform; inactive tiles of an inverse pass are
+// zero-filled on the way.  Returns -1 when none is left.
+IB_HD int64_t pkp_next_active(const IlPassArgs &a, int64_t t, int64_t step, int64_t ntiles, int tid, int nt) {
+    for (; t < ntiles; t += step) {
+        if (pkp_tile_active(a, t)) return t;
+        if (a.win_mode == 2) pkp_tile_zero_fill(a, t, tid, nt);
+    }
+    return -1;
+}
+
 // registers the in-place middle stage needs per thread (complex pairs); the persistent form is used
 // when this stays within 16 (N <= 512 with the radices of IB200_FFT_SPEC_LIST)
 IB_HD constexpr int pkp_mid_pairs(int n, int r1, int r2, int nt) { return r2 > 1 ? ((kSpecL / 2 * (n / r1) + nt - 1) / nt) * r1 : 0; }
@@ -423,7 +465,11 @@ IB_HD void fft_pkp_tile_body(const IlPassArgs &a, int64_t tile, int64_t next, fl
     constexpr bool THREE = R2 > 1;
     PkPrefCtx<SWAP_IN, SWAP_OUT> c;
     c.raw = raw; c.gout = const_cast<c64 *>(pkp_tile_base(a, tile)); c.tw = a.tw; c.pstride = a.pstride;
-    c.in0 = a.in0; c.inlen = (unsigned)(a.in1 - a.in0); c.out0 = a.out0; c.outlen = (unsigned)(a.out1 - a.out0);
+    int lo, hi;
+    pkp_tile_window(a, tile, true, lo, hi);
+    c.in0 = lo; c.inlen = (unsigned)(hi - lo);
+    pkp_tile_window(a, tile, false, lo, hi);
+    c.out0 = lo; c.outlen = (unsigned)(hi - lo);
     pk_stage<N, R0, 1, true, false, NT>(c, nullptr, bufA, tid, nt);
     IB_SYNC();                                                       // raw[] consumed, bufA complete
     if (next >= 0) pkp_prefetch(a, next, raw, tid, nt);

@@ -232,6 +232,68 @@ static int launch_kb_gather(cudaStream_t s, int64_t m, int C, c64 alpha, const K
     return 0;
 }
 
+// ---- k-space support windows ---------------------------------------------------------------------------
+// A trajectory touches only part of the oversampled grid (a radial "kooshball" the inscribed sphere,
+// 52 % of the cube; a stack of spirals a cylinder).  Grid points outside the support are never read
+// by G' and are exactly zero in G'^H k, so the last forward FFT pass need not write them, the adjoint
+// gather need not store zeros for them and the first inverse pass need not read them.  Per block of
+// bx x by grid columns the support is summarised as one interval [lo, hi) along z (hull over the
+// block, rounded to multiples of tz so that whole tiles of the stored adjoint fall inside or outside).
+__global__ void __launch_bounds__(256) support_init_kernel(int n, int32_t *lo, int32_t *hi) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { lo[i] = 0x7fffffff; hi[i] = 0; }
+}
+
+__global__ void __launch_bounds__(256) support_mark_kernel(int64_t kp, const int32_t *__restrict__ rowptr,
+                                                           const int32_t *__restrict__ rowmap, int n0, int n1, int n2,
+                                                           int bx, int by, int tz, int nbx, int32_t *lo, int32_t *hi) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= kp) return;
+    if (rowptr[r + 1] == rowptr[r]) return;
+    const int64_t g = rowmap[r];
+    if (g < 0) return;
+    const int x = (int)(g % n0), y = (int)((g / n0) % n1), z = (int)(g / ((int64_t)n0 * n1));
+    const int b = (y / by) * nbx + x / bx;
+    const int zl = (z / tz) * tz;
+    int zh = zl + tz; if (zh > n2) zh = n2;
+    atomicMin(lo + b, zl);
+    atomicMax(hi + b, zh);
+}
+
+__global__ void __launch_bounds__(256) support_expand_kernel(int n0, int n1, int bx, int by, int nbx,
+                                                             const int32_t *__restrict__ lo,
+                                                             const int32_t *__restrict__ hi, int32_t *__restrict__ win,
+                                                             unsigned long long *inside) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long mine = 0;
+    if (p < n0 * n1) {
+        const int x = p % n0, y = p / n0;
+        const int b = (y / by) * nbx + x / bx;
+        int l = lo[b], h = hi[b];
+        if (h <= l) { l = 0; h = 0; }
+        win[2 * p] = l; win[2 * p + 1] = h;
+        mine = (unsigned long long)(h - l);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(inside, mine);
+}
+
+__global__ void __launch_bounds__(256) support_rowmap_kernel(int64_t kp, const int32_t *__restrict__ rowmap, int n0, int n1,
+                                                             const int32_t *__restrict__ win,
+                                                             int32_t *__restrict__ rowmap_out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= kp) return;
+    const int64_t g = rowmap[r];
+    int32_t out = -1;
+    if (g >= 0) {
+        const int64_t p = g % ((int64_t)n0 * n1);
+        const int z = (int)(g / ((int64_t)n0 * n1));
+        if (z >= win[2 * p] && z < win[2 * p + 1]) out = (int32_t)g;
+    }
+    rowmap_out[r] = out;
+}
+
 static int kb_pow2_ceil(int64_t v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 }  // namespace ib200
@@ -266,6 +328,43 @@ int ib200_kb_records(void *stream, int64_t m, const double *coord, const int64_t
     cudaFree(flag);
     IB200_TRY(e);
     IB200_TRY(cudaGetLastError());
+    return 0;
+}
+
+int ib200_grid_support_windows(void *stream, const int64_t grid[3], int64_t kp, const int32_t *rowptr,
+                               const int32_t *rowmap, const int64_t block[3], int32_t *win, int32_t *rowmap_out,
+                               int64_t *host_inside) {
+    IB200_REQUIRE(grid && block && host_inside, "null pointer");
+    *host_inside = 0;
+    IB200_REQUIRE(grid[0] > 0 && grid[1] > 0 && grid[2] > 0 && grid[0] * grid[1] < (1LL << 30), "bad grid");
+    IB200_REQUIRE(block[0] > 0 && block[1] > 0 && block[2] > 0, "bad block");
+    IB200_REQUIRE(kp >= 0 && kp < (1LL << 31), "bad row count");
+    IB200_REQUIRE(rowptr && rowmap && win && rowmap_out, "null pointer");
+    const int n0 = (int)grid[0], n1 = (int)grid[1], n2 = (int)grid[2];
+    const int bx = (int)block[0], by = (int)block[1], tz = (int)block[2];
+    const int nbx = (n0 + bx - 1) / bx, nby = (n1 + by - 1) / by, nb = nbx * nby;
+    cudaStream_t s = as_stream(stream);
+    int32_t *lo = nullptr;
+    unsigned long long *inside = nullptr;
+    IB200_TRY(cudaMalloc(&lo, (size_t)nb * 2 * sizeof(int32_t) + 16));
+    int32_t *hi = lo + nb;
+    cudaError_t e = cudaMalloc(&inside, sizeof(unsigned long long));
+    if (e != cudaSuccess) { cudaFree(lo); IB200_TRY(e); }
+    cudaMemsetAsync(inside, 0, sizeof(unsigned long long), s);
+    support_init_kernel<<<(unsigned)ceil_div(nb, 256), 256, 0, s>>>(nb, lo, hi);
+    if (kp > 0)
+        support_mark_kernel<<<(unsigned)ceil_div(kp, 256), 256, 0, s>>>(kp, rowptr, rowmap, n0, n1, n2, bx, by, tz, nbx, lo, hi);
+    support_expand_kernel<<<(unsigned)ceil_div((int64_t)n0 * n1, 256), 256, 0, s>>>(n0, n1, bx, by, nbx, lo, hi, win, inside);
+    if (kp > 0)
+        support_rowmap_kernel<<<(unsigned)ceil_div(kp, 256), 256, 0, s>>>(kp, rowmap, n0, n1, win, rowmap_out);
+    count_launch(4);
+    unsigned long long h = 0;
+    cudaMemcpyAsync(&h, inside, sizeof(h), cudaMemcpyDeviceToHost, s);
+    e = cudaStreamSynchronize(s);
+    cudaFree(lo); cudaFree(inside);
+    IB200_TRY(e);
+    IB200_TRY(cudaGetLastError());
+    *host_inside = (int64_t)h;
     return 0;
 }
 

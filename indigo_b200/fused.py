@@ -38,6 +38,8 @@ class SenseDevice(object):
     staged_fwd = -41
     staged_adj = -4
     allow_separable = True     # forward gridding from 96-byte separable-weight records instead of stored entries
+    allow_windows = True       # k-space support windows: skip the grid outside the trajectory's support
+    window_min_saving = 0.05   # ... when at least this fraction of the grid lies outside
 
     def __init__(self, B, N, coord, maps, oversamp=2.0, weights=None, width=3, n=128):
         from .sense import gridding_matrix_device, _fftc_mod, kb_records_device
@@ -121,7 +123,30 @@ class SenseDevice(object):
         if self.nlong:
             self.longrows = B.empty_array((self.nlong,), i32, name='G.H.longrows')
             lib.csr_long_rows(s, kp, self.t_ptr.ptr, self.long_thresh, self.longrows.ptr, self.nlong, ctypes.byref(cnt))
-        self.grid = B.empty_array((self.on * C,), _C64, name='grid[z][y][x][c]')
+        # k-space support windows (csrc/kbgrid.cu, csrc/fft_pk.cuh): grid points no sample touches are neither
+        # written by the last forward pass, nor zero-filled by the adjoint gather, nor read by the first
+        # inverse pass.  Blocks of bx x 4 columns share one z interval; 16 interleaved lines (one FFT tile)
+        # must not straddle two blocks.
+        self.win, self.support_fraction = None, 1.0
+        if self.allow_windows and self.nnz and (C % 16 == 0 or 16 % C == 0):
+            bx = max(self.tile[0], 16 // C) if C < 16 else self.tile[0]
+            if self.oN[0] % bx == 0 and bx % self.tile[0] == 0:
+                win = B.empty_array((2 * self.oN[0] * self.oN[1],), i32, name='G.support')
+                rowmap_w = B.empty_array((kp,), i32, name='G.H.rowmap.support')
+                inside = ctypes.c_int64()
+                blk = (ctypes.c_int64 * 3)(bx, self.tile[1], self.tile[2])
+                lib.grid_support_windows(s, grid3, kp, self.t_ptr.ptr, self.rowmap.ptr, blk, win.ptr, rowmap_w.ptr,
+                                         ctypes.byref(inside))
+                frac = inside.value / float(self.on)
+                if frac <= 1.0 - self.window_min_saving:
+                    try:
+                        lib.sense_plan_set_support(self._plan, win.ptr, bx)
+                        self.win, self.rowmap, self.support_fraction = win, rowmap_w, frac
+                    except RuntimeError:
+                        pass                                            # geometry without persistent packed z passes
+        # zero-initialised: with windows, parts of the grid are never written, and the separable gather
+        # multiplies its zero-weight taps (6th tap of on-grid samples) with whatever is there
+        self.grid = B.zero_array((self.on * C,), _C64, name='grid[z][y][x][c]')
         self.ksp = B.empty_array((self.M * C,), _C64, name='ksp[m][c]')
         if C > 32:
             raise RuntimeError("fused SENSE path serves at most 32 coils per operator; shard or split the coils")

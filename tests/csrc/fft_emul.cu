@@ -78,8 +78,12 @@ extern "C" int emul_fft(int ndim, const int64_t *dims, int64_t batch, float *y, 
 
 // ---- fused SENSE transforms on the interleaved grid (fft_il.cuh + windowed strided passes) ----
 // Mirrors ib200_sense_expand_fft / ib200_sense_ifft_combine of fft.cu pass by pass.
+static const int32_t *g_win = nullptr;       // optional support windows of the z passes (emul_sense_set_windows)
+static int g_win_div = 1;
+extern "C" void emul_sense_set_windows(const int32_t *win, int div) { g_win = win; g_win_div = div; }
+
 static int emul_strided(const AxisPlan &ax, c64 *base, int64_t inner, int64_t outer, int64_t outer_stride, int in0,
-                        int in1, int out0, int out1, int swap_in, int swap_out) {
+                        int in1, int out0, int out1, int swap_in, int swap_out, int win_mode = 0) {
     FftKernelArgs k;
     k.x = base; k.y = base; k.tw = ax.tw_dev; k.din = k.dout = nullptr; k.conj_in = k.conj_out = 0;
     k.plane = 0; k.n = ax.n; k.L = kSpecL; k.log2L = 4; k.swap_in = swap_in; k.swap_out = swap_out;
@@ -91,6 +95,7 @@ static int emul_strided(const AxisPlan &ax, c64 *base, int64_t inner, int64_t ou
         IlPassArgs a;
         a.x = base; a.tw = ax.tw_dev; a.inner = inner; a.outer = outer; a.outer_stride = outer_stride;
         a.pstride = (unsigned)inner; a.in0 = in0; a.in1 = in1; a.out0 = out0; a.out1 = out1;
+        if (win_mode && g_win) { a.win = g_win; a.win_mode = win_mode; a.win_div = g_win_div; }
         if (getenv("IB200_FFT_NOPK") == nullptr && (outer_stride & 1) == 0) {   // same choice as try_pk_pass (fft.cu)
 #define EMUL_PK(n, r0, r1, r2)                                                                     \
             if (!done && fft_spec_matches(k, n, r0, r1, r2)) {                                     \
@@ -101,6 +106,7 @@ static int emul_strided(const AxisPlan &ax, c64 *base, int64_t inner, int64_t ou
                 std::vector<c64> raw((size_t)n * kSpecL + 2);                                      \
                 for (int64_t b = 0; b < nb; ++b) {                                                 \
                     if (pkp) {      /* persistent form: prefetch of tile b, then the tile body (next = none) */ \
+                        if (pkp_next_active(a, b, 1, b + 1, 0, 1) < 0) continue;                   \
                         for (auto &v : raw) v = mk(NAN, NAN);                                      \
                         pkp_prefetch(a, b, raw.data(), 0, 1);                                      \
                         if (swap_in)       fft_pkp_tile_body<n, r0, r1, r2, true, false, 0>(a, b, -1, sp.data(), raw.data(), 0, 1); \
@@ -182,10 +188,10 @@ extern "C" int emul_sense(const int64_t *N, const int64_t *oN, int64_t C, int wh
         if (!done) return IB200_E_UNSUPPORTED;
         rc = emul_strided(pl.ax[1], (c64 *)grid + off[2] * sz, sy, N[2], sz, (int)off[1], (int)(off[1] + N[1]), 0, (int)oN[1], 0, 0);
         if (rc) return rc;
-        return emul_strided(pl.ax[2], (c64 *)grid, sz, 1, sz * oN[2], (int)off[2], (int)(off[2] + N[2]), 0, (int)oN[2], 0, 0);
+        return emul_strided(pl.ax[2], (c64 *)grid, sz, 1, sz * oN[2], (int)off[2], (int)(off[2] + N[2]), 0, (int)oN[2], 0, 0, 1);
     }
     // inverse FFT + combine
-    rc = emul_strided(pl.ax[2], (c64 *)grid, sz, 1, sz * oN[2], 0, (int)oN[2], (int)off[2], (int)(off[2] + N[2]), 1, 0);
+    rc = emul_strided(pl.ax[2], (c64 *)grid, sz, 1, sz * oN[2], 0, (int)oN[2], (int)off[2], (int)(off[2] + N[2]), 1, 0, 2);
     if (rc) return rc;
     rc = emul_strided(pl.ax[1], (c64 *)grid + off[2] * sz, sy, N[2], sz, 0, (int)oN[1], (int)off[1], (int)(off[1] + N[1]), 0, 0);
     if (rc) return rc;

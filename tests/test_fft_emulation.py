@@ -135,3 +135,55 @@ def test_fused_sense_expand_and_combine(emul_sense, N, oN, C):
     grid = np.ascontiguousarray(g.transpose(2, 1, 0, 3))
     emul_sense(1, N, oN, C, grid, y_d, pf_d, 1.0, 0.0)
     assert rel(y_d.transpose(2, 1, 0), (np.conj(pf) * inv[sl]).sum(axis=3)) < 5e-7
+
+
+@pytest.mark.parametrize("N,oN,C,bx", [((16, 16, 16), (32, 32, 32), 16, 4), ((16, 26, 16), (32, 52, 32), 4, 4),
+                                       ((16, 16, 13), (32, 32, 52), 2, 8), ((16, 16, 16), (32, 32, 32), 32, 4)])
+def test_fused_sense_support_windows(emul_sense, N, oN, C, bx):
+    """Per-column k-space support windows of the z passes (csrc/fft_pk.cuh): the forward transform writes the
+    grid only inside the windows (and there it equals the full transform), the inverse transform reads it only
+    inside them (NaNs outside must not matter) and treats the rest as zero."""
+    if os.environ.get("IB200_FFT_NOPK") or os.environ.get("IB200_FFT_NOPKP"):
+        pytest.skip("windows need the persistent packed passes")
+    lib = ctypes.CDLL(SO)
+    rs = np.random.RandomState(3 + C)
+    nbx, nby = oN[0] // bx, oN[1] // 4
+    lo = rs.randint(0, oN[2] // 2, size=(nby, nbx)) // 4 * 4
+    hi = np.minimum(oN[2], lo + rs.randint(0, oN[2], size=(nby, nbx)) // 4 * 4)
+    hi[0, 0] = lo[0, 0]                                     # at least one empty block
+    win = np.zeros((oN[1], oN[0], 2), dtype=np.int32)       # [y][x] -> (lo, hi)
+    for y in range(oN[1]):
+        for x in range(oN[0]):
+            l, h = lo[y // 4, x // bx], hi[y // 4, x // bx]
+            win[y, x] = (l, h) if h > l else (0, 0)
+    inside = np.zeros(tuple(oN), dtype=bool)                # [x, y, z]
+    for y in range(oN[1]):
+        for x in range(oN[0]):
+            inside[x, y, win[y, x, 0]:win[y, x, 1]] = True
+    img = _crand(rs, *N); pf = _crand(rs, *N, C)
+    off = [o // 2 - n // 2 for n, o in zip(N, oN)]
+    sl = tuple(slice(o, o + n) for o, n in zip(off, N))
+    pad = np.zeros(tuple(oN) + (C,), dtype=np.complex128)
+    pad[sl] = (pf * img[..., None]).astype(np.complex128)
+    want = np.fft.fftn(pad, axes=(0, 1, 2))
+    img_d = np.ascontiguousarray(img.transpose(2, 1, 0)); pf_d = np.ascontiguousarray(pf.transpose(2, 1, 0, 3))
+    lib.emul_sense_set_windows(win.ctypes.data_as(ctypes.c_void_p), C)
+    try:
+        grid = np.full((oN[2], oN[1], oN[0], C), np.nan + 0j, dtype=np.complex64)
+        emul_sense(0, N, oN, C, grid, img_d, pf_d)
+        got = grid.transpose(2, 1, 0, 3)
+        assert rel(got[inside], want[inside]) < 5e-7
+        # outside the windows nothing of the LAST pass was written: planes the earlier passes never touch stay NaN
+        zout = np.ones(oN[2], dtype=bool); zout[off[2]:off[2] + N[2]] = False
+        assert np.isnan(got[:, :, zout][~inside[:, :, zout]]).all()
+        # inverse: NaN outside the windows must be ignored (treated as zero)
+        g = _crand(rs, *oN, C)
+        gz = np.where(inside[..., None], g, 0).astype(np.complex128)
+        gn = np.where(inside[..., None], g, np.nan + 0j).astype(np.complex64)
+        grid = np.ascontiguousarray(gn.transpose(2, 1, 0, 3))
+        inv = np.fft.ifftn(gz, axes=(0, 1, 2)) * np.prod(oN)
+        y_d = np.full(N[::-1], np.nan + 0j, dtype=np.complex64)
+        emul_sense(1, N, oN, C, grid, y_d, pf_d, 1.0, 0.0)
+        assert rel(y_d.transpose(2, 1, 0), (np.conj(pf) * inv[sl]).sum(axis=3)) < 5e-7
+    finally:
+        lib.emul_sense_set_windows(None, 1)

@@ -43,17 +43,23 @@ def _setup(N, C, traj, weighted, seed=0):
     return rs, coord, maps, w
 
 
-@pytest.mark.parametrize("mode", ["separable", "real-packed", "complex"])
+@pytest.mark.parametrize("mode", ["separable", "separable-nowindows", "real-packed", "complex"])
 @pytest.mark.parametrize("N,C,traj,weighted", CASES)
 def test_fused_against_oracle(B, N, C, traj, weighted, mode, monkeypatch):
     from indigo_b200 import fused
     real = mode != "complex"
     monkeypatch.setattr(fused.SenseDevice, "allow_real", real)
-    monkeypatch.setattr(fused.SenseDevice, "allow_separable", mode == "separable")
+    monkeypatch.setattr(fused.SenseDevice, "allow_separable", mode.startswith("separable"))
+    monkeypatch.setattr(fused.SenseDevice, "allow_windows", mode != "separable-nowindows")
+    monkeypatch.setattr(fused.SenseDevice, "window_min_saving", 0.0)
     rs, coord, maps, w = _setup(N, C, traj, weighted)
     A = sense_operator_fused(B, N, coord, maps, 2.0, weights=w)
     assert A._dev.real == real
-    assert (A._dev.kb is not None) == (mode == "separable")
+    assert (A._dev.kb is not None) == mode.startswith("separable")
+    if mode == "separable-nowindows":
+        assert A._dev.win is None
+    elif C % 2 == 0 and (C % 16 == 0 or 16 % C == 0):
+        assert A._dev.win is not None and 0.0 < A._dev.support_fraction <= 1.0
     ref = osense.SenseOperator(N, coord, maps, 2.0, weights=w)
     nvox = int(np.prod(N))
     x = synth.rand64c(rs, nvox, 1)
