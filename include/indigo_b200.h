@@ -149,6 +149,11 @@ int ib200_csr_permute_rows(void *stream, int64_t m, int64_t nnz, const int32_t *
  * CTA instead of one lane group.  nlong == 0 disables the split. */
 int ib200_csr_long_rows(void *stream, int64_t m, const int32_t *rowptr, int thresh, int32_t *list, int capacity,
                         int *host_count);
+/* Two-level form: tiles grouped into super-tiles of super[0] x super[1] x super[2] tiles (super-tile major,
+ * then tile major, then point).  Only colrank is produced (NULL: size query); used as the sort key of the
+ * samples for ib200_csr_permute_rows so that the samples in flight cover a compact, L2-sized block. */
+int ib200_grid_tile_rank2(void *stream, const int64_t grid[3], const int64_t tile[3], const int64_t super[3],
+                          int32_t *colrank, int64_t *nranks);
 int ib200_grid_tile_rank(void *stream, const int64_t grid[3], const int64_t tile[3], int32_t *colrank, int32_t *rowmap,
                          int64_t *padded_rows);
 /* Separable Kaiser-Bessel gridding (the product ccsrmm(G') of the -O3 SENSE tree, SURVEY.md 3.1,
@@ -169,6 +174,23 @@ int ib200_kb_records(void *stream, int64_t m, const double *coord, const int64_t
                      const float *f2, const int32_t *perm, void *records, int *host_flag);
 int ib200_kb_gather(void *stream, int64_t m, int64_t ncols, float alpha_re, float alpha_im, const void *records,
                     const void *grid_il, int64_t xpitch, const int64_t grid[3], void *Yil, int64_t ypitch);
+/* x-run form of a stored adjoint in tile-major row order (fused SENSE recipe, csrc/csrmm_runs.cu): the four
+ * consecutive rows that form one x-row of a 4x4x4 tile are merged into one list of (sample, 4 weights)
+ * entries, padded to a multiple of four entries.  ib200_csr_runs_count fills run_ptr[kp/4 + 1] and returns
+ * the number of run entries and the number of rows that belong to runs whose four rows hold more than
+ * long_thresh entries together (those runs get no list: their rows go to the long-row kernel);
+ * ib200_csr_runs_fill writes ids[entries] (int32), w4[entries] (4 floats each) and the long-row list.
+ * ib200_ccsrmm_runs computes Yil[rowmap[r]][c] = alpha * sum_p w(r,p) * Xil[col(r,p)][c] for all kp rows
+ * (rowmap < 0: nothing stored) with an even number of interleaved columns.  `packed`/`rowptr` are the
+ * packed entries and row pointers the runs were built from.  The first two synchronise. */
+int ib200_csr_runs_count(void *stream, int64_t kp, const int32_t *rowptr, const void *packed, int long_thresh,
+                         int32_t *run_ptr, int64_t *host_entries, int *host_longrows);
+int ib200_csr_runs_fill(void *stream, int64_t kp, const int32_t *rowptr, const void *packed, int long_thresh,
+                        const int32_t *run_ptr, int32_t *ids, void *w4, int32_t *longrows, int capacity);
+int ib200_ccsrmm_runs(void *stream, int64_t kp, int64_t ncols, float alpha_re, float alpha_im, const int32_t *run_ptr,
+                      const int32_t *ids, const void *w4, const void *Xil, int64_t xpitch, void *Yil, int64_t ypitch,
+                      const int32_t *rowmap, const int32_t *rowptr, const void *packed, const int32_t *longrows,
+                      int nlong, int long_thresh);
 /* k-space support windows of a trajectory (fused SENSE recipe only).  Given the stored adjoint of the
  * gridding matrix in tile-major row order (rowptr[kp+1], rowmap[kp] from ib200_grid_tile_rank) the
  * grid columns are grouped into blocks of block[0] x block[1] points; for each block the hull [lo, hi)

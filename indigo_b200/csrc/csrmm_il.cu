@@ -388,6 +388,14 @@ static int launch_long(cudaStream_t s, int CL, int nlong, const int32_t *longrow
     return 0;
 }
 
+// entry point for csrmm_runs.cu: long rows of a packed real-weight matrix
+int launch_long_packed(cudaStream_t s, int CL, int nlong, const int32_t *longrows, int C, c64 alpha, const void *ent,
+                       const int32_t *rowptr, const c64 *Xil, int64_t xpitch, c64 *Yil, int64_t ypitch,
+                       const int32_t *rowmap) {
+    return launch_long<true>(s, CL, nlong, longrows, C, alpha, ent, nullptr, nullptr, rowptr, Xil, xpitch, Yil, ypitch,
+                             rowmap);
+}
+
 // ---------------------------------------------------------------------------
 // Staged variant of the real-weight gather (north star: "column indices staged through shared
 // memory").  A CTA owns R = GPB*RPG consecutive rows, i.e. one contiguous range of packed entries;
@@ -600,6 +608,28 @@ __global__ void __launch_bounds__(256) tile_rank_kernel(int n0, int n1, int n2, 
     }
 }
 
+// two-level variant: tiles of t0 x t1 x t2 points grouped into super-tiles of s0 x s1 x s2 tiles; rank =
+// super-tile major, then tile major inside the super-tile, then point inside the tile.  Used as the sort
+// key of the SAMPLES: the CTAs in flight at any time (a few thousand consecutive samples each) then
+// cover a compact block of the grid whose lines stay in L2, instead of a 13-plane slab of the whole grid.
+__global__ void __launch_bounds__(256) tile_rank2_kernel(int n0, int n1, int n2, int t0, int t1, int t2, int s0, int s1,
+                                                         int s2, int32_t *__restrict__ colrank) {
+    const int64_t total = (int64_t)n0 * n1 * n2;
+    const int nt0 = (n0 + t0 - 1) / t0, nt1 = (n1 + t1 - 1) / t1;
+    const int ns0 = (nt0 + s0 - 1) / s0, ns1 = (nt1 + s1 - 1) / s1;
+    const int tvol = t0 * t1 * t2, svol = s0 * s1 * s2;
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += nth) {
+        const int x = (int)(g % n0), y = (int)((g / n0) % n1), z = (int)(g / ((int64_t)n0 * n1));
+        const int tx = x / t0, ty = y / t1, tz = z / t2;
+        const int sx = tx / s0, sy = ty / s1, sz = tz / s2;
+        const int64_t super = ((int64_t)sz * ns1 + sy) * ns0 + sx;
+        const int intile = ((z % t2) * t1 + (y % t1)) * t0 + (x % t0);
+        const int insuper = ((tz % s2) * s1 + (ty % s1)) * s0 + (tx % s0);
+        colrank[g] = (int32_t)((super * svol + insuper) * tvol + intile);
+    }
+}
+
 static int pow2_ceil(int64_t v) { int p = 1; while (p < v) p <<= 1; return p; }
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
@@ -708,6 +738,27 @@ int ib200_grid_tile_rank(void *stream, const int64_t grid[3], const int64_t tile
     int64_t g = ceil_div(padded, 256); const int64_t cap = (int64_t)sm_count() * 16; if (g > cap) g = cap;
     tile_rank_kernel<<<(unsigned)g, 256, 0, as_stream(stream)>>>((int)grid[0], (int)grid[1], (int)grid[2], (int)tile[0],
                                                                 (int)tile[1], (int)tile[2], colrank, rowmap);
+    IB200_LAUNCH_CHECK();
+    return 0;
+}
+
+int ib200_grid_tile_rank2(void *stream, const int64_t grid[3], const int64_t tile[3], const int64_t super[3],
+                          int32_t *colrank, int64_t *nranks) {
+    IB200_REQUIRE(grid && tile && super && nranks, "null pointer");
+    int64_t padded = 1;
+    for (int d = 0; d < 3; ++d) {
+        IB200_REQUIRE(grid[d] > 0 && tile[d] > 0 && tile[d] <= 64 && super[d] > 0 && super[d] <= 64, "bad grid / tile extent");
+        const int64_t nt = ceil_div(grid[d], tile[d]);
+        padded *= ceil_div(nt, super[d]) * super[d] * tile[d];
+    }
+    IB200_REQUIRE(padded < (1LL << 31), "padded grid must hold fewer than 2^31 points");
+    *nranks = padded;
+    if (!colrank) return 0;
+    const int64_t total = grid[0] * grid[1] * grid[2];
+    int64_t g = ceil_div(total, 256); const int64_t cap = (int64_t)sm_count() * 16; if (g > cap) g = cap;
+    tile_rank2_kernel<<<(unsigned)g, 256, 0, as_stream(stream)>>>((int)grid[0], (int)grid[1], (int)grid[2], (int)tile[0],
+                                                                 (int)tile[1], (int)tile[2], (int)super[0], (int)super[1],
+                                                                 (int)super[2], colrank);
     IB200_LAUNCH_CHECK();
     return 0;
 }

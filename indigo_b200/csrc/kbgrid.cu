@@ -146,11 +146,17 @@ __global__ void __launch_bounds__(256, 3) kb_gather_kernel(int64_t m, int C, c64
     const char *gb = reinterpret_cast<const char *>(grid + (coil_ok ? coil : 0));
     const uint64_t rowbytes = (uint64_t)n0 * pitch;
     const bool dense_pitch = pitch == (uint32_t)PITCH;
-    const int64_t s0 = ((int64_t)blockIdx.x * 8 + warp) * (int64_t)(SPW * iters);
+    // the 8 warps of the CTA sweep its records together (32 consecutive samples per step): what is in L1
+    // at any time is the footprint of one or two neighbouring tiles, not of 8 unrelated ones
+    const int64_t s0 = (int64_t)blockIdx.x * (int64_t)(8 * SPW * iters) + warp * SPW;
     for (int it = 0; it < iters; ++it) {
-        const int64_t rbase = s0 + (int64_t)it * SPW;
+        const int64_t rbase = s0 + (int64_t)it * (8 * SPW);
         if (rbase >= m) break;                                       // warp-uniform
         const int64_t r = rbase + slot;
+        if (sub == 0 && r + 8 * SPW < m) {                           // next step's record: two lines, pulled into L2 now
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + r + 8 * SPW));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(rec + r + 8 * SPW) + 64));
+        }
         float wx[kKbTaps], wy[kKbTaps], wz[kKbTaps];
         int ix0 = 0, iy0 = 0, iz0 = 0, out = -1, nt = 0;
         if (r < m) {

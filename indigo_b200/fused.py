@@ -32,17 +32,27 @@ class SenseDevice(object):
     tile = (4, 4, 4)
     allow_real = True          # use the real-weight packed kernels when the matrix values are real
     long_thresh = 512          # rows of G'^H with more entries than this get a whole CTA each
-    sample_tile = (8, 8, 8)    # samples (rows of G') are sorted by the grid tile of this size they fall into
+    sample_tile = (8, 8, 8)    # samples (rows of G') are sorted by the grid tile of this size they fall into,
+    sample_super = (8, 8, 8)   # tiles grouped into super-tiles of this many tiles (64^3 points: L2-sized working set)
     # rows_per_group codes of ib200_ccsrmm_ilr (measured on cfg3, profiles/r01_s5_*): shared-memory staged
     # entries; one coil per lane for the long forward rows, two coils per lane for the short adjoint rows
     staged_fwd = -41
     staged_adj = -4
     allow_separable = True     # forward gridding from 96-byte separable-weight records instead of stored entries
+    allow_runs = True          # adjoint gridding on merged x-runs of the stored adjoint (csrc/csrmm_runs.cu)
+    run_long_thresh = 2048     # runs whose four rows hold more entries than this go to the long-row kernel
     allow_windows = True       # k-space support windows: skip the grid outside the trajectory's support
     window_min_saving = 0.05   # ... when at least this fraction of the grid lies outside
 
     def __init__(self, B, N, coord, maps, oversamp=2.0, weights=None, width=3, n=128):
+        import os
         from .sense import gridding_matrix_device, _fftc_mod, kb_records_device
+        if os.environ.get("IB200_SAMPLE_SUPER"):                    # tuning knob: super-tile edge in tiles
+            self.sample_super = (int(os.environ["IB200_SAMPLE_SUPER"]),) * 3
+        if os.environ.get("IB200_SAMPLE_TILE"):                     # tuning knob: sample tile edge in grid points
+            self.sample_tile = (int(os.environ["IB200_SAMPLE_TILE"]),) * 3
+        if os.environ.get("IB200_RUN_LONG"):                        # tuning knob (tools/): run-length threshold
+            self.run_long_thresh = int(os.environ["IB200_RUN_LONG"])
         from .host.noncart import rolloff3
 
         self.B = B
@@ -97,11 +107,12 @@ class SenseDevice(object):
                 # samples sorted by the 8x8x8 grid tile they fall into: the rows one CTA owns then share
                 # operand lines in all three dimensions (L1) and neighbouring CTAs share them in L2
                 stile = (ctypes.c_int64 * 3)(*self.sample_tile)
-                lib.grid_tile_rank(s, grid3, stile, None, None, ctypes.byref(padded))
+                ssuper = (ctypes.c_int64 * 3)(*self.sample_super)
+                lib.grid_tile_rank2(s, grid3, stile, ssuper, None, ctypes.byref(padded))
                 nr8 = int(padded.value)
                 rank8 = B.empty_array((self.on,), i32)
-                junk = B.empty_array((nr8,), i32)
-                lib.grid_tile_rank(s, grid3, stile, rank8.ptr, junk.ptr, ctypes.byref(padded))
+                junk = None
+                lib.grid_tile_rank2(s, grid3, stile, ssuper, rank8.ptr, ctypes.byref(padded))
                 self.g_ptr = B.empty_array((self.M + 1,), i32, name='G.sorted.rowPtrs')
                 self.g_pk = B.zero_array((self.nnz + 2,), pk, name='G.sorted.packed')
                 self.g_map = B.empty_array((max(self.M, 1),), i32, name='G.sorted.rowmap')
@@ -144,6 +155,20 @@ class SenseDevice(object):
                         self.win, self.rowmap, self.support_fraction = win, rowmap_w, frac
                     except RuntimeError:
                         pass                                            # geometry without persistent packed z passes
+        # x-run lists of the stored adjoint: one gather of a sample serves the four grid points of a tile row
+        self.runs = None
+        if self.real and self.allow_runs and C % 2 == 0 and self.tile[0] == 4 and kp % 4 == 0:
+            run_ptr = B.empty_array((kp // 4 + 1,), i32, name='G.H.runs.ptr')
+            nre, nlr = ctypes.c_int64(), ctypes.c_int()
+            lib.csr_runs_count(s, kp, self.t_ptr.ptr, self.t_pk.ptr, self.run_long_thresh, run_ptr.ptr,
+                               ctypes.byref(nre), ctypes.byref(nlr))
+            ne = max(int(nre.value), 4)
+            ids = B.empty_array((ne,), i32, name='G.H.runs.ids')
+            w4 = B.empty_array((4 * ne,), np.dtype('float32'), name='G.H.runs.w4')
+            lrows = B.empty_array((max(int(nlr.value), 1),), i32, name='G.H.runs.longrows')
+            lib.csr_runs_fill(s, kp, self.t_ptr.ptr, self.t_pk.ptr, self.run_long_thresh, run_ptr.ptr, ids.ptr, w4.ptr,
+                              lrows.ptr, int(nlr.value))
+            self.runs = (run_ptr, ids, w4, lrows, int(nlr.value), int(nre.value))
         # zero-initialised: with windows, parts of the grid are never written, and the separable gather
         # multiplies its zero-weight taps (6th tap of on-grid samples) with whatever is there
         self.grid = B.zero_array((self.on * C,), _C64, name='grid[z][y][x][c]')
@@ -178,7 +203,12 @@ class SenseDevice(object):
     def samples_to_grid(self):
         lib, s = self.B._lib, self.B._stream
         lr = self.longrows.ptr if self.nlong else None
-        if self.real:
+        if self.real and self.runs is not None:
+            run_ptr, ids, w4, lrows, nlr, _ = self.runs
+            lib.ccsrmm_runs(s, self.kp, self.C, 1.0, 0.0, run_ptr.ptr, ids.ptr, w4.ptr, self.ksp.ptr, self.C,
+                            self.grid.ptr, self.C, self.rowmap.ptr, self.t_ptr.ptr, self.t_pk.ptr,
+                            lrows.ptr if nlr else None, nlr, self.run_long_thresh)
+        elif self.real:
             lib.ccsrmm_ilr(s, self.kp, self.M, self.C, self.nnz, 1.0, 0.0, self.t_pk.ptr, self.t_ptr.ptr,
                            self.ksp.ptr, self.C, self.grid.ptr, self.C, self.rowmap.ptr, self.staged_adj, lr, self.nlong,
                            self.long_thresh)

@@ -51,6 +51,7 @@ def test_fused_against_oracle(B, N, C, traj, weighted, mode, monkeypatch):
     monkeypatch.setattr(fused.SenseDevice, "allow_real", real)
     monkeypatch.setattr(fused.SenseDevice, "allow_separable", mode.startswith("separable"))
     monkeypatch.setattr(fused.SenseDevice, "allow_windows", mode != "separable-nowindows")
+    monkeypatch.setattr(fused.SenseDevice, "allow_runs", mode.startswith("separable"))
     monkeypatch.setattr(fused.SenseDevice, "window_min_saving", 0.0)
     rs, coord, maps, w = _setup(N, C, traj, weighted)
     A = sense_operator_fused(B, N, coord, maps, 2.0, weights=w)
@@ -82,6 +83,31 @@ def test_fused_against_oracle(B, N, C, traj, weighted, mode, monkeypatch):
     kd = B.copy_array(np.full((ref.M * C, 1), np.nan, dtype=C64, order='F'))
     A.eval(kd, B.copy_array(x), alpha=2.0)
     assert relerr(kd.to_host(), 2.0 * ref.forward(x)) < TOL
+
+
+@pytest.mark.parametrize("runs", [True, False], ids=["x-runs", "rows"])
+@pytest.mark.parametrize("C", [16, 4, 6])
+def test_fused_long_rows(B, C, runs, monkeypatch):
+    """Rows / runs of the stored adjoint above the length threshold go to the one-CTA-per-row kernel (the
+    k-space centre of a radial trajectory): thresholds forced low so that small problems exercise it."""
+    from indigo_b200 import fused
+    monkeypatch.setattr(fused.SenseDevice, "allow_runs", runs)
+    monkeypatch.setattr(fused.SenseDevice, "long_thresh", 6)
+    monkeypatch.setattr(fused.SenseDevice, "run_long_thresh", 24)
+    monkeypatch.setattr(fused.SenseDevice, "window_min_saving", 0.0)
+    N = (16, 16, 16)
+    rs = np.random.RandomState(11 + C)
+    coord = synth.kooshball_3d(nspokes=128, nread=32)
+    maps = synth.unit_rss_maps(rs, N, C)
+    A = sense_operator_fused(B, N, coord, maps, 2.0)
+    d = A._dev
+    assert (d.runs is not None) == runs
+    assert (d.runs[4] if runs else d.nlong) > 0
+    ref = osense.SenseOperator(N, coord, maps, 2.0)
+    x = synth.rand64c(rs, int(np.prod(N)), 1)
+    y = synth.rand64c(rs, ref.M * C, 1)
+    assert relerr(A.H * y, ref.adjoint(y)) < TOL
+    assert relerr(normal_operator(A) * x, ref.normal(x)) < TOL
 
 
 def test_fused_cg_iterates(B):
