@@ -177,20 +177,20 @@ int ib200_kb_gather(void *stream, int64_t m, int64_t ncols, float alpha_re, floa
 /* x-run form of a stored adjoint in tile-major row order (fused SENSE recipe, csrc/csrmm_runs.cu): the four
  * consecutive rows that form one x-row of a 4x4x4 tile are merged into one list of (sample, 4 weights)
  * entries, padded to a multiple of four entries.  ib200_csr_runs_count fills run_ptr[kp/4 + 1] and returns
- * the number of run entries and the number of rows that belong to runs whose four rows hold more than
- * long_thresh entries together (those runs get no list: their rows go to the long-row kernel);
- * ib200_csr_runs_fill writes ids[entries] (int32), w4[entries] (4 floats each) and the long-row list.
+ * the number of run entries, and -- for runs longer than seg_len entries, which are cut into segments
+ * of seg_len -- the number of segments and of such runs; ib200_csr_runs_fill writes ids[entries] (int32),
+ * w4[entries] (4 floats each), seg_desc[4*segments] and split_desc[4*split runs] (int32 quadruples).
  * ib200_ccsrmm_runs computes Yil[rowmap[r]][c] = alpha * sum_p w(r,p) * Xil[col(r,p)][c] for all kp rows
- * (rowmap < 0: nothing stored) with an even number of interleaved columns.  `packed`/`rowptr` are the
- * packed entries and row pointers the runs were built from.  The first two synchronise. */
-int ib200_csr_runs_count(void *stream, int64_t kp, const int32_t *rowptr, const void *packed, int long_thresh,
-                         int32_t *run_ptr, int64_t *host_entries, int *host_longrows);
-int ib200_csr_runs_fill(void *stream, int64_t kp, const int32_t *rowptr, const void *packed, int long_thresh,
-                        const int32_t *run_ptr, int32_t *ids, void *w4, int32_t *longrows, int capacity);
+ * (rowmap < 0: nothing stored) with an even number of interleaved columns; `scratch` holds the partial
+ * sums of the segments: segments * 4 * 2*pow2ceil(ncols/2) complex words.  The first two synchronise. */
+int ib200_csr_runs_count(void *stream, int64_t kp, const int32_t *rowptr, const void *packed, int seg_len,
+                         int32_t *run_ptr, int64_t *host_entries, int *host_segments, int *host_split);
+int ib200_csr_runs_fill(void *stream, int64_t kp, const int32_t *rowptr, const void *packed, int seg_len,
+                        const int32_t *run_ptr, int32_t *ids, void *w4, int32_t *seg_desc, int32_t *split_desc);
 int ib200_ccsrmm_runs(void *stream, int64_t kp, int64_t ncols, float alpha_re, float alpha_im, const int32_t *run_ptr,
                       const int32_t *ids, const void *w4, const void *Xil, int64_t xpitch, void *Yil, int64_t ypitch,
-                      const int32_t *rowmap, const int32_t *rowptr, const void *packed, const int32_t *longrows,
-                      int nlong, int long_thresh);
+                      const int32_t *rowmap, int seg_len, const int32_t *seg_desc, int nseg, const int32_t *split_desc,
+                      int nsplit, void *scratch);
 /* k-space support windows of a trajectory (fused SENSE recipe only).  Given the stored adjoint of the
  * gridding matrix in tile-major row order (rowptr[kp+1], rowmap[kp] from ib200_grid_tile_rank) the
  * grid columns are grouped into blocks of block[0] x block[1] points; for each block the hull [lo, hi)

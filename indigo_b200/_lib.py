@@ -49,9 +49,9 @@ SIGNATURES = {
     "ib200_kb_gather": (_i, [_vp, _i64, _i64, _f, _f, _vp, _vp, _i64, POINTER(_i64), _vp, _i64]),
     "ib200_grid_support_windows": (_i, [_vp, POINTER(_i64), _i64, _vp, _vp, POINTER(_i64), _vp, _vp, POINTER(_i64)]),
     "ib200_sense_plan_set_support": (_i, [_vp, _vp, _i]),
-    "ib200_csr_runs_count": (_i, [_vp, _i64, _vp, _vp, _i, _vp, POINTER(_i64), POINTER(_i)]),
-    "ib200_csr_runs_fill": (_i, [_vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i]),
-    "ib200_ccsrmm_runs": (_i, [_vp, _i64, _i64, _f, _f, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i, _i]),
+    "ib200_csr_runs_count": (_i, [_vp, _i64, _vp, _vp, _i, _vp, POINTER(_i64), POINTER(_i), POINTER(_i)]),
+    "ib200_csr_runs_fill": (_i, [_vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "ib200_ccsrmm_runs": (_i, [_vp, _i64, _i64, _f, _f, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i, _vp, _i, _vp, _i, _vp]),
     "ib200_grid_tile_rank2": (_i, [_vp, POINTER(_i64), POINTER(_i64), POINTER(_i64), _vp, POINTER(_i64)]),
     "ib200_grid_tile_rank": (_i, [_vp, POINTER(_i64), POINTER(_i64), _vp, _vp, POINTER(_i64)]),
     "ib200_csr_inspect": (_i, [_vp, _i64, _i64, _vp, _vp, _vp, POINTER(_i64)]),

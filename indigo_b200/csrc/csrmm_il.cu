@@ -388,14 +388,6 @@ static int launch_long(cudaStream_t s, int CL, int nlong, const int32_t *longrow
     return 0;
 }
 
-// entry point for csrmm_runs.cu: long rows of a packed real-weight matrix
-int launch_long_packed(cudaStream_t s, int CL, int nlong, const int32_t *longrows, int C, c64 alpha, const void *ent,
-                       const int32_t *rowptr, const c64 *Xil, int64_t xpitch, c64 *Yil, int64_t ypitch,
-                       const int32_t *rowmap) {
-    return launch_long<true>(s, CL, nlong, longrows, C, alpha, ent, nullptr, nullptr, rowptr, Xil, xpitch, Yil, ypitch,
-                             rowmap);
-}
-
 // ---------------------------------------------------------------------------
 // Staged variant of the real-weight gather (north star: "column indices staged through shared
 // memory").  A CTA owns R = GPB*RPG consecutive rows, i.e. one contiguous range of packed entries;

@@ -13,8 +13,10 @@
 // the sampled region instead of 12, so the per-row overhead is paid a quarter as often.  Lists are
 // padded to multiples of four entries (weight 0) so that the loop has no tail.
 //
-// Runs longer than `long_thresh` entries (k-space centre of radial trajectories) are left out; their
-// rows are listed for csrmm_il_long_kernel, which gives each of them a whole CTA.
+// Runs longer than `seg_len` entries (the k-space centre of a radial trajectory collects up to ~10^5
+// samples in one run) are cut into segments of seg_len entries: every segment is walked by its own lane
+// group into a scratch row of partial sums, and a last small kernel adds the partial sums of each such
+// run in segment order, so the result does not depend on scheduling.
 #include "common.cuh"
 #include "pk2.cuh"
 
@@ -50,47 +52,39 @@ __device__ __forceinline__ int run_merge(const int32_t *__restrict__ rowptr, con
     return n;
 }
 
-__device__ __forceinline__ bool run_is_long(const int32_t *__restrict__ rowptr, int64_t r, int long_thresh) {
-    // the merged list holds at most the sum of the four rows: a cheap, conservative bound
-    return rowptr[kRun * r + kRun] - rowptr[kRun * r] > long_thresh;
-}
-
 __global__ void __launch_bounds__(128) run_count_kernel(int64_t nruns, const int32_t *__restrict__ rowptr,
-                                                        const RunPacked *__restrict__ ent, int long_thresh,
-                                                        int32_t *__restrict__ counts, int *nlongrows) {
+                                                        const RunPacked *__restrict__ ent, int seg_len,
+                                                        int32_t *__restrict__ counts, int *totals) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nruns) return;
-    if (run_is_long(rowptr, r, long_thresh)) {
-        counts[r] = 0;
-        int c = 0;
-#pragma unroll
-        for (int i = 0; i < kRun; ++i) c += rowptr[kRun * r + i + 1] > rowptr[kRun * r + i];
-        atomicAdd(nlongrows, c);
-        return;
-    }
     const int n = run_merge(rowptr, ent, r, nullptr, nullptr);
-    counts[r] = (n + kRunPad - 1) / kRunPad * kRunPad;
+    const int padded = (n + kRunPad - 1) / kRunPad * kRunPad;
+    counts[r] = padded;
+    if (padded > seg_len) { atomicAdd(totals, (padded + seg_len - 1) / seg_len); atomicAdd(totals + 1, 1); }
 }
 
+// lists of one run; runs longer than seg_len also get their segment descriptors {run, first entry, end
+// entry, 0} and one split descriptor {run, first segment, segments, 0}
 __global__ void __launch_bounds__(128) run_fill_kernel(int64_t nruns, const int32_t *__restrict__ rowptr,
-                                                       const RunPacked *__restrict__ ent, int long_thresh,
+                                                       const RunPacked *__restrict__ ent, int seg_len,
                                                        const int32_t *__restrict__ run_ptr, int32_t *__restrict__ ids,
-                                                       float4 *__restrict__ w4, int32_t *__restrict__ longrows,
-                                                       int capacity, int *nlongrows) {
+                                                       float4 *__restrict__ w4, int4 *__restrict__ seg_desc,
+                                                       int4 *__restrict__ split_desc, int *cursors) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nruns) return;
-    if (run_is_long(rowptr, r, long_thresh)) {
-#pragma unroll
-        for (int i = 0; i < kRun; ++i)
-            if (rowptr[kRun * r + i + 1] > rowptr[kRun * r + i]) {
-                const int at = atomicAdd(nlongrows, 1);
-                if (at < capacity) longrows[at] = (int32_t)(kRun * r + i);
-            }
-        return;
-    }
     const int a = run_ptr[r], b = run_ptr[r + 1];
     const int n = run_merge(rowptr, ent, r, ids + a, w4 + a);
     for (int q = a + n; q < b; ++q) { ids[q] = n ? ids[a + n - 1] : 0; w4[q] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    if (b - a > seg_len) {
+        const int k = (b - a + seg_len - 1) / seg_len;
+        const int s0 = atomicAdd(cursors, k);
+        const int at = atomicAdd(cursors + 1, 1);
+        for (int j = 0; j < k; ++j) {
+            const int sa = a + j * seg_len;
+            seg_desc[s0 + j] = make_int4((int)r, sa, sa + seg_len < b ? sa + seg_len : b, 0);
+        }
+        split_desc[at] = make_int4((int)r, s0, k, 0);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -102,16 +96,57 @@ __device__ __forceinline__ void run_load_batch(RunBatch &e, const int32_t *__res
     for (int u = 0; u < kRunPad; ++u) e.w[u] = __ldcs(w4 + p + u);
 }
 
+// acc[t][0..1] += sum over the run entries [a, b) of w_t * X[id]  (two coils per lane, b - a a multiple of 4)
+__device__ __forceinline__ void run_walk(int a, int b, const int32_t *__restrict__ ids, const float4 *__restrict__ w4,
+                                         const char *xb, uint32_t xpitch_bytes, pk2 (&acc)[kRun][2]) {
+    RunBatch e;
+    run_load_batch(e, ids, w4, a);
+    for (int p = a; p < b; p += kRunPad) {
+        float4 x[kRunPad];
+        const int idv[kRunPad] = {e.id.x, e.id.y, e.id.z, e.id.w};
+#pragma unroll
+        for (int u = 0; u < kRunPad; ++u)
+            x[u] = __ldg(reinterpret_cast<const float4 *>(xb + (uint64_t)(uint32_t)idv[u] * xpitch_bytes));
+        RunBatch nx;
+        const bool more = p + kRunPad < b;
+        if (more) run_load_batch(nx, ids, w4, p + kRunPad);
+#pragma unroll
+        for (int u = 0; u < kRunPad; ++u) {
+            const pk2 x0 = p_make(x[u].x, x[u].y), x1 = p_make(x[u].z, x[u].w);
+            const float wv[kRun] = {e.w[u].x, e.w[u].y, e.w[u].z, e.w[u].w};
+#pragma unroll
+            for (int t = 0; t < kRun; ++t) {
+                acc[t][0] = p_fma(p_bc(wv[t]), x0, acc[t][0]);
+                acc[t][1] = p_fma(p_bc(wv[t]), x1, acc[t][1]);
+            }
+        }
+        if (more) e = nx;
+    }
+}
+
+__device__ __forceinline__ void run_store(const pk2 (&acc)[kRun][2], c64 alpha, const int32_t *__restrict__ rowmap,
+                                          int64_t run, c64 *__restrict__ Yil, int64_t ypitch, int coil) {
+#pragma unroll
+    for (int t = 0; t < kRun; ++t) {
+        const int64_t out = (int64_t)__ldg(rowmap + kRun * run + t);
+        if (out >= 0) {
+            const c64 o0 = cmul(alpha, mk(p_lo(acc[t][0]), p_hi(acc[t][0])));
+            const c64 o1 = cmul(alpha, mk(p_lo(acc[t][1]), p_hi(acc[t][1])));
+            __stcs(reinterpret_cast<float4 *>(Yil + out * ypitch + coil), make_float4(o0.x, o0.y, o1.x, o1.y));
+        }
+    }
+}
+
 // Yil[rowmap[4*run + i]][c] = alpha * sum_e w_i(e) * Xil[id(e)][c]        (rowmap < 0: nothing stored)
-// CL lanes per run, two coils per lane (one 16-byte gather per run entry and lane).
+// CL lanes per run, two coils per lane (one 16-byte gather per run entry and lane).  Runs longer than
+// seg_len are left to the segment kernels below.
 template <int CL>
 __global__ void __launch_bounds__(256) csrmm_runs_kernel(int64_t nruns, int C, c64 alpha,
                                                          const int32_t *__restrict__ run_ptr,
                                                          const int32_t *__restrict__ ids, const float4 *__restrict__ w4,
                                                          const c64 *__restrict__ Xil, uint32_t xpitch_bytes,
                                                          c64 *__restrict__ Yil, int64_t ypitch,
-                                                         const int32_t *__restrict__ rowmap,
-                                                         const int32_t *__restrict__ rowptr, int long_thresh, int rpg) {
+                                                         const int32_t *__restrict__ rowmap, int seg_len, int rpg) {
     constexpr int GPB = 256 / CL;
     const int gl = (int)(threadIdx.x & (CL - 1)), group = (int)(threadIdx.x / CL);
     const int coil = 2 * gl;
@@ -124,7 +159,9 @@ __global__ void __launch_bounds__(256) csrmm_runs_kernel(int64_t nruns, int C, c
         // an L2 hit instead of a DRAM round trip each.
         const int64_t first = (int64_t)blockIdx.x * ((int64_t)GPB * rpg);
         const int64_t last = first + (int64_t)GPB * rpg < nruns ? first + (int64_t)GPB * rpg : nruns;
-        const int e0 = __ldg(run_ptr + first), e1 = __ldg(run_ptr + last);
+        const int e0 = __ldg(run_ptr + first);
+        int e1 = __ldg(run_ptr + last);
+        if (e1 - e0 > 64 * 1024) e1 = e0 + 64 * 1024;                // split runs: their segments prefetch for themselves
         for (int q = e0 + 8 * (int)threadIdx.x; q < e1; q += 8 * 256)        // 128 bytes of weights, 32 of ids
             asm volatile("prefetch.global.L2 [%0];" ::"l"(w4 + q));
         for (int q = e0 + 32 * (int)threadIdx.x; q < e1; q += 32 * 256)
@@ -134,55 +171,67 @@ __global__ void __launch_bounds__(256) csrmm_runs_kernel(int64_t nruns, int C, c
         const int64_t run = run0 + (int64_t)i * GPB;
         if (run >= nruns) break;
         const int a = __ldg(run_ptr + run), b = __ldg(run_ptr + run + 1);
+        if (b - a > seg_len) continue;
         pk2 acc[kRun][2];
 #pragma unroll
         for (int t = 0; t < kRun; ++t) { acc[t][0] = p_make(0.f, 0.f); acc[t][1] = p_make(0.f, 0.f); }
-        if (a < b) {
-            RunBatch e;
-            run_load_batch(e, ids, w4, a);
-            for (int p = a; p < b; p += kRunPad) {
-                float4 x[kRunPad];
-                const int idv[kRunPad] = {e.id.x, e.id.y, e.id.z, e.id.w};
-#pragma unroll
-                for (int u = 0; u < kRunPad; ++u)
-                    x[u] = __ldg(reinterpret_cast<const float4 *>(xb + (uint64_t)(uint32_t)idv[u] * xpitch_bytes));
-                RunBatch nx;
-                const bool more = p + kRunPad < b;
-                if (more) run_load_batch(nx, ids, w4, p + kRunPad);
-#pragma unroll
-                for (int u = 0; u < kRunPad; ++u) {
-                    const pk2 x0 = p_make(x[u].x, x[u].y), x1 = p_make(x[u].z, x[u].w);
-                    const float wv[kRun] = {e.w[u].x, e.w[u].y, e.w[u].z, e.w[u].w};
-#pragma unroll
-                    for (int t = 0; t < kRun; ++t) {
-                        acc[t][0] = p_fma(p_bc(wv[t]), x0, acc[t][0]);
-                        acc[t][1] = p_fma(p_bc(wv[t]), x1, acc[t][1]);
-                    }
-                }
-                if (more) e = nx;
-            }
-        }
-        // rows of a long run belong to csrmm_il_long_kernel, except its empty rows, which nobody else visits
-        const bool is_long = a == b && run_is_long(rowptr, run, long_thresh);
-        if (coil_ok) {
-#pragma unroll
-            for (int t = 0; t < kRun; ++t) {
-                if (is_long && __ldg(rowptr + kRun * run + t + 1) > __ldg(rowptr + kRun * run + t)) continue;
-                const int64_t out = (int64_t)__ldg(rowmap + kRun * run + t);
-                if (out >= 0) {
-                    const c64 o0 = cmul(alpha, mk(p_lo(acc[t][0]), p_hi(acc[t][0])));
-                    const c64 o1 = cmul(alpha, mk(p_lo(acc[t][1]), p_hi(acc[t][1])));
-                    __stcs(reinterpret_cast<float4 *>(Yil + out * ypitch + coil), make_float4(o0.x, o0.y, o1.x, o1.y));
-                }
-            }
-        }
+        if (a < b) run_walk(a, b, ids, w4, xb, xpitch_bytes, acc);
+        if (coil_ok) run_store(acc, alpha, rowmap, run, Yil, ypitch, coil);
     }
 }
 
+// one lane group per segment of a split run: partial sums into scratch[seg][t][coil]
+template <int CL>
+__global__ void __launch_bounds__(256) csrmm_runs_seg_kernel(int nseg, int C, const int4 *__restrict__ seg_desc,
+                                                             const int32_t *__restrict__ ids,
+                                                             const float4 *__restrict__ w4, const c64 *__restrict__ Xil,
+                                                             uint32_t xpitch_bytes, c64 *__restrict__ scratch, int cpitch) {
+    constexpr int GPB = 256 / CL;
+    const int gl = (int)(threadIdx.x & (CL - 1)), group = (int)(threadIdx.x / CL);
+    const int coil = 2 * gl;
+    const int sidx = blockIdx.x * GPB + group;
+    if (sidx >= nseg) return;
+    const int4 d = __ldg(seg_desc + sidx);
+    const char *xb = reinterpret_cast<const char *>(Xil + (coil < C ? coil : 0));
+    pk2 acc[kRun][2];
+#pragma unroll
+    for (int t = 0; t < kRun; ++t) { acc[t][0] = p_make(0.f, 0.f); acc[t][1] = p_make(0.f, 0.f); }
+    run_walk(d.y, d.z, ids, w4, xb, xpitch_bytes, acc);
+    if (coil < C) {
+#pragma unroll
+        for (int t = 0; t < kRun; ++t)
+            *reinterpret_cast<float4 *>(scratch + ((int64_t)sidx * kRun + t) * cpitch + coil) =
+                make_float4(p_lo(acc[t][0]), p_hi(acc[t][0]), p_lo(acc[t][1]), p_hi(acc[t][1]));
+    }
+}
+
+// one lane group per split run: partial sums added in segment order, then stored like any other run
+template <int CL>
+__global__ void __launch_bounds__(256) csrmm_runs_fold_kernel(int nsplit, int C, c64 alpha, const int4 *__restrict__ split_desc,
+                                                              const c64 *__restrict__ scratch, int cpitch,
+                                                              c64 *__restrict__ Yil, int64_t ypitch,
+                                                              const int32_t *__restrict__ rowmap) {
+    constexpr int GPB = 256 / CL;
+    const int gl = (int)(threadIdx.x & (CL - 1)), group = (int)(threadIdx.x / CL);
+    const int coil = 2 * gl;
+    const int idx = blockIdx.x * GPB + group;
+    if (idx >= nsplit || coil >= C) return;
+    const int4 d = __ldg(split_desc + idx);
+    pk2 acc[kRun][2];
+#pragma unroll
+    for (int t = 0; t < kRun; ++t) { acc[t][0] = p_make(0.f, 0.f); acc[t][1] = p_make(0.f, 0.f); }
+    for (int sgm = d.y; sgm < d.y + d.z; ++sgm) {
+#pragma unroll
+        for (int t = 0; t < kRun; ++t) {
+            const float4 v = *reinterpret_cast<const float4 *>(scratch + ((int64_t)sgm * kRun + t) * cpitch + coil);
+            acc[t][0] = p_add(acc[t][0], p_make(v.x, v.y));
+            acc[t][1] = p_add(acc[t][1], p_make(v.z, v.w));
+        }
+    }
+    run_store(acc, alpha, rowmap, d.x, Yil, ypitch, coil);
+}
+
 int exclusive_scan_public(cudaStream_t s, int64_t n, const int32_t *in, int32_t *out);   // csrmm.cu
-int launch_long_packed(cudaStream_t s, int CL, int nlong, const int32_t *longrows, int C, c64 alpha, const void *ent,
-                       const int32_t *rowptr, const c64 *Xil, int64_t xpitch, c64 *Yil, int64_t ypitch,
-                       const int32_t *rowmap);                                          // csrmm_il.cu
 
 static int runs_pow2_ceil(int64_t v) { int p = 1; while (p < v) p <<= 1; return p; }
 
@@ -192,55 +241,60 @@ using namespace ib200;
 
 extern "C" {
 
-int ib200_csr_runs_count(void *stream, int64_t kp, const int32_t *rowptr, const void *packed, int long_thresh,
-                         int32_t *run_ptr, int64_t *host_entries, int *host_longrows) {
+int ib200_csr_runs_count(void *stream, int64_t kp, const int32_t *rowptr, const void *packed, int seg_len,
+                         int32_t *run_ptr, int64_t *host_entries, int *host_segments, int *host_split) {
     IB200_REQUIRE(kp >= 0 && kp % kRun == 0 && kp < (1LL << 31), "row count must be a multiple of 4");
-    IB200_REQUIRE(host_entries && host_longrows && long_thresh >= 0, "bad arguments");
-    *host_entries = 0; *host_longrows = 0;
+    IB200_REQUIRE(host_entries && host_segments && host_split, "null pointer");
+    IB200_REQUIRE(seg_len >= kRunPad && seg_len % kRunPad == 0, "segment length must be a positive multiple of 4");
+    *host_entries = 0; *host_segments = 0; *host_split = 0;
     if (kp == 0) return 0;
     IB200_REQUIRE(rowptr && packed && run_ptr, "null pointer");
     const int64_t nruns = kp / kRun;
     cudaStream_t s = as_stream(stream);
     int32_t *counts = nullptr;
-    IB200_TRY(cudaMalloc(&counts, (size_t)(nruns + 1) * sizeof(int32_t) + sizeof(int)));
-    int *nlong = reinterpret_cast<int *>(counts + nruns + 1);
-    cudaMemsetAsync(nlong, 0, sizeof(int), s);
-    run_count_kernel<<<(unsigned)ceil_div(nruns, 128), 128, 0, s>>>(nruns, rowptr, (const RunPacked *)packed, long_thresh,
-                                                                   counts, nlong);
+    IB200_TRY(cudaMalloc(&counts, (size_t)(nruns + 1) * sizeof(int32_t) + 2 * sizeof(int)));
+    int *totals = reinterpret_cast<int *>(counts + nruns + 1);
+    cudaMemsetAsync(totals, 0, 2 * sizeof(int), s);
+    run_count_kernel<<<(unsigned)ceil_div(nruns, 128), 128, 0, s>>>(nruns, rowptr, (const RunPacked *)packed, seg_len, counts,
+                                                                   totals);
     count_launch();
     int rc = exclusive_scan_public(s, nruns, counts, run_ptr);
     int32_t total = 0;
-    int hl = 0;
+    int ht[2] = {0, 0};
     cudaError_t e = cudaSuccess;
     if (!rc) {
         cudaMemcpyAsync(&total, run_ptr + nruns, sizeof(int32_t), cudaMemcpyDeviceToHost, s);
-        cudaMemcpyAsync(&hl, nlong, sizeof(int), cudaMemcpyDeviceToHost, s);
+        cudaMemcpyAsync(ht, totals, sizeof(ht), cudaMemcpyDeviceToHost, s);
         e = cudaStreamSynchronize(s);
     }
     cudaFree(counts);
     if (rc) return rc;
     IB200_TRY(e);
     IB200_TRY(cudaGetLastError());
-    *host_entries = total; *host_longrows = hl;
+    IB200_REQUIRE(total >= 0, "run lists exceed 2^31 entries");
+    *host_entries = total; *host_segments = ht[0]; *host_split = ht[1];
     return 0;
 }
 
-int ib200_csr_runs_fill(void *stream, int64_t kp, const int32_t *rowptr, const void *packed, int long_thresh,
-                        const int32_t *run_ptr, int32_t *ids, void *w4, int32_t *longrows, int capacity) {
+int ib200_csr_runs_fill(void *stream, int64_t kp, const int32_t *rowptr, const void *packed, int seg_len,
+                        const int32_t *run_ptr, int32_t *ids, void *w4, int32_t *seg_desc, int32_t *split_desc) {
     IB200_REQUIRE(kp >= 0 && kp % kRun == 0 && kp < (1LL << 31), "row count must be a multiple of 4");
+    IB200_REQUIRE(seg_len >= kRunPad && seg_len % kRunPad == 0, "segment length must be a positive multiple of 4");
     if (kp == 0) return 0;
-    IB200_REQUIRE(rowptr && packed && run_ptr && ids && w4 && (longrows || capacity == 0), "null pointer");
-    IB200_REQUIRE(((uintptr_t)ids & 15) == 0 && ((uintptr_t)w4 & 15) == 0, "run arrays must be 16-byte aligned");
+    IB200_REQUIRE(rowptr && packed && run_ptr && ids && w4 && seg_desc && split_desc, "null pointer");
+    IB200_REQUIRE(((uintptr_t)ids & 15) == 0 && ((uintptr_t)w4 & 15) == 0 && ((uintptr_t)seg_desc & 15) == 0 &&
+                  ((uintptr_t)split_desc & 15) == 0, "run arrays must be 16-byte aligned");
     const int64_t nruns = kp / kRun;
     cudaStream_t s = as_stream(stream);
-    int *nlong = nullptr;
-    IB200_TRY(cudaMalloc(&nlong, sizeof(int)));
-    cudaMemsetAsync(nlong, 0, sizeof(int), s);
-    run_fill_kernel<<<(unsigned)ceil_div(nruns, 128), 128, 0, s>>>(nruns, rowptr, (const RunPacked *)packed, long_thresh,
-                                                                  run_ptr, ids, (float4 *)w4, longrows, capacity, nlong);
+    int *cursors = nullptr;
+    IB200_TRY(cudaMalloc(&cursors, 2 * sizeof(int)));
+    cudaMemsetAsync(cursors, 0, 2 * sizeof(int), s);
+    run_fill_kernel<<<(unsigned)ceil_div(nruns, 128), 128, 0, s>>>(nruns, rowptr, (const RunPacked *)packed, seg_len, run_ptr,
+                                                                  ids, (float4 *)w4, (int4 *)seg_desc, (int4 *)split_desc,
+                                                                  cursors);
     count_launch();
     cudaError_t e = cudaStreamSynchronize(s);
-    cudaFree(nlong);
+    cudaFree(cursors);
     IB200_TRY(e);
     IB200_TRY(cudaGetLastError());
     return 0;
@@ -248,34 +302,43 @@ int ib200_csr_runs_fill(void *stream, int64_t kp, const int32_t *rowptr, const v
 
 int ib200_ccsrmm_runs(void *stream, int64_t kp, int64_t ncols, float ar, float ai, const int32_t *run_ptr,
                       const int32_t *ids, const void *w4, const void *Xil, int64_t xpitch, void *Yil, int64_t ypitch,
-                      const int32_t *rowmap, const int32_t *rowptr, const void *packed, const int32_t *longrows,
-                      int nlong, int long_thresh) {
+                      const int32_t *rowmap, int seg_len, const int32_t *seg_desc, int nseg, const int32_t *split_desc,
+                      int nsplit, void *scratch) {
     IB200_REQUIRE(kp >= 0 && kp % kRun == 0 && kp < (1LL << 31), "row count must be a multiple of 4");
     if (kp == 0 || ncols == 0) return 0;
     IB200_REQUIRE(ncols > 0 && ncols <= 64 && ncols % 2 == 0, "run gather serves an even number of at most 64 columns");
-    IB200_REQUIRE(run_ptr && ids && w4 && Xil && Yil && rowmap && rowptr, "null pointer");
+    IB200_REQUIRE(run_ptr && ids && w4 && Xil && Yil && rowmap, "null pointer");
     IB200_REQUIRE(xpitch >= ncols && ypitch >= ncols && xpitch % 2 == 0 && ypitch % 2 == 0, "bad pitch");
     IB200_REQUIRE(((uintptr_t)Xil & 15) == 0 && ((uintptr_t)Yil & 15) == 0, "operands must be 16-byte aligned");
     IB200_REQUIRE(xpitch * (int64_t)sizeof(c64) < (1LL << 32), "operand pitch too large");
+    IB200_REQUIRE(seg_len >= kRunPad && nseg >= 0 && nsplit >= 0, "bad segment arguments");
+    IB200_REQUIRE(nseg == 0 || (seg_desc && split_desc && scratch && ((uintptr_t)scratch & 15) == 0), "segment arrays missing");
     const int64_t nruns = kp / kRun;
     const c64 alpha = mk(ar, ai);
     cudaStream_t s = as_stream(stream);
-    if (nlong > 0) {
-        IB200_REQUIRE(longrows && packed, "long-row list / packed entries missing");
-        const int rc = launch_long_packed(s, runs_pow2_ceil(ncols), nlong, longrows, (int)ncols, alpha, packed, rowptr,
-                                          (const c64 *)Xil, xpitch, (c64 *)Yil, ypitch, rowmap);
-        if (rc) return rc;
-    }
     const int CL = runs_pow2_ceil(ncols / 2);
     const int rpg = 4;
-    const int64_t per_cta = (int64_t)(256 / CL) * rpg;
-    const int64_t blocks = ceil_div(nruns, per_cta);
+    const int GPB = 256 / CL;
+    const int64_t blocks = ceil_div(nruns, (int64_t)GPB * rpg);
     IB200_REQUIRE(blocks < (1LL << 31), "too many runs for one launch");
+    const int cpitch = 2 * CL;                                       // scratch row: 2*CL complex words per point
+    const uint32_t pb = (uint32_t)(xpitch * sizeof(c64));
 #define IB200_RUNS_CASE(cl)                                                                                            \
     case cl:                                                                                                           \
+        if (nseg > 0) {                                                                                                \
+            csrmm_runs_seg_kernel<cl><<<(unsigned)ceil_div(nseg, GPB), 256, 0, s>>>(nseg, (int)ncols, (const int4 *)seg_desc, ids, \
+                                                                                   (const float4 *)w4, (const c64 *)Xil, pb,  \
+                                                                                   (c64 *)scratch, cpitch);           \
+            count_launch();                                                                                            \
+        }                                                                                                              \
         csrmm_runs_kernel<cl><<<(unsigned)blocks, 256, 0, s>>>(nruns, (int)ncols, alpha, run_ptr, ids, (const float4 *)w4, \
-                                                               (const c64 *)Xil, (uint32_t)(xpitch * sizeof(c64)), (c64 *)Yil, \
-                                                               ypitch, rowmap, rowptr, long_thresh, rpg);             \
+                                                               (const c64 *)Xil, pb, (c64 *)Yil, ypitch, rowmap, seg_len, rpg); \
+        if (nsplit > 0) {                                                                                              \
+            count_launch();                                                                                            \
+            csrmm_runs_fold_kernel<cl><<<(unsigned)ceil_div(nsplit, GPB), 256, 0, s>>>(nsplit, (int)ncols, alpha,      \
+                                                                                      (const int4 *)split_desc, (const c64 *)scratch, \
+                                                                                      cpitch, (c64 *)Yil, ypitch, rowmap); \
+        }                                                                                                              \
         break
     switch (CL) {
         IB200_RUNS_CASE(1); IB200_RUNS_CASE(2); IB200_RUNS_CASE(4); IB200_RUNS_CASE(8); IB200_RUNS_CASE(16); IB200_RUNS_CASE(32);

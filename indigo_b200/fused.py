@@ -40,7 +40,7 @@ class SenseDevice(object):
     staged_adj = -4
     allow_separable = True     # forward gridding from 96-byte separable-weight records instead of stored entries
     allow_runs = True          # adjoint gridding on merged x-runs of the stored adjoint (csrc/csrmm_runs.cu)
-    run_long_thresh = 2048     # runs whose four rows hold more entries than this go to the long-row kernel
+    run_long_thresh = 1024     # runs with more entries than this are cut into segments of this length
     allow_windows = True       # k-space support windows: skip the grid outside the trajectory's support
     window_min_saving = 0.05   # ... when at least this fraction of the grid lies outside
 
@@ -155,20 +155,27 @@ class SenseDevice(object):
                         self.win, self.rowmap, self.support_fraction = win, rowmap_w, frac
                     except RuntimeError:
                         pass                                            # geometry without persistent packed z passes
-        # x-run lists of the stored adjoint: one gather of a sample serves the four grid points of a tile row
+        # x-run lists of the stored adjoint: one gather of a sample serves the four grid points of a tile row;
+        # runs longer than run_long_thresh entries are cut into segments with their own lane groups
         self.runs = None
         if self.real and self.allow_runs and C % 2 == 0 and self.tile[0] == 4 and kp % 4 == 0:
+            seg = max(4, int(self.run_long_thresh) // 4 * 4)
             run_ptr = B.empty_array((kp // 4 + 1,), i32, name='G.H.runs.ptr')
-            nre, nlr = ctypes.c_int64(), ctypes.c_int()
-            lib.csr_runs_count(s, kp, self.t_ptr.ptr, self.t_pk.ptr, self.run_long_thresh, run_ptr.ptr,
-                               ctypes.byref(nre), ctypes.byref(nlr))
-            ne = max(int(nre.value), 4)
+            nre, nsg, nsp = ctypes.c_int64(), ctypes.c_int(), ctypes.c_int()
+            lib.csr_runs_count(s, kp, self.t_ptr.ptr, self.t_pk.ptr, seg, run_ptr.ptr,
+                               ctypes.byref(nre), ctypes.byref(nsg), ctypes.byref(nsp))
+            ne, nsg, nsp = max(int(nre.value), 4), int(nsg.value), int(nsp.value)
             ids = B.empty_array((ne,), i32, name='G.H.runs.ids')
             w4 = B.empty_array((4 * ne,), np.dtype('float32'), name='G.H.runs.w4')
-            lrows = B.empty_array((max(int(nlr.value), 1),), i32, name='G.H.runs.longrows')
-            lib.csr_runs_fill(s, kp, self.t_ptr.ptr, self.t_pk.ptr, self.run_long_thresh, run_ptr.ptr, ids.ptr, w4.ptr,
-                              lrows.ptr, int(nlr.value))
-            self.runs = (run_ptr, ids, w4, lrows, int(nlr.value), int(nre.value))
+            segd = B.empty_array((4 * max(nsg, 1),), i32, name='G.H.runs.segments')
+            spld = B.empty_array((4 * max(nsp, 1),), i32, name='G.H.runs.split')
+            lib.csr_runs_fill(s, kp, self.t_ptr.ptr, self.t_pk.ptr, seg, run_ptr.ptr, ids.ptr, w4.ptr, segd.ptr, spld.ptr)
+            cl = 1
+            while cl < C // 2:
+                cl *= 2
+            scratch = B.empty_array((max(nsg, 1) * 4 * 2 * cl,), _C64, name='G.H.runs.partial')
+            self.runs = dict(ptr=run_ptr, ids=ids, w4=w4, seg=seg, segd=segd, nseg=nsg, spld=spld, nsplit=nsp,
+                             scratch=scratch, entries=int(nre.value))
         # zero-initialised: with windows, parts of the grid are never written, and the separable gather
         # multiplies its zero-weight taps (6th tap of on-grid samples) with whatever is there
         self.grid = B.zero_array((self.on * C,), _C64, name='grid[z][y][x][c]')
@@ -204,10 +211,10 @@ class SenseDevice(object):
         lib, s = self.B._lib, self.B._stream
         lr = self.longrows.ptr if self.nlong else None
         if self.real and self.runs is not None:
-            run_ptr, ids, w4, lrows, nlr, _ = self.runs
-            lib.ccsrmm_runs(s, self.kp, self.C, 1.0, 0.0, run_ptr.ptr, ids.ptr, w4.ptr, self.ksp.ptr, self.C,
-                            self.grid.ptr, self.C, self.rowmap.ptr, self.t_ptr.ptr, self.t_pk.ptr,
-                            lrows.ptr if nlr else None, nlr, self.run_long_thresh)
+            r = self.runs
+            lib.ccsrmm_runs(s, self.kp, self.C, 1.0, 0.0, r['ptr'].ptr, r['ids'].ptr, r['w4'].ptr, self.ksp.ptr, self.C,
+                            self.grid.ptr, self.C, self.rowmap.ptr, r['seg'], r['segd'].ptr, r['nseg'], r['spld'].ptr,
+                            r['nsplit'], r['scratch'].ptr)
         elif self.real:
             lib.ccsrmm_ilr(s, self.kp, self.M, self.C, self.nnz, 1.0, 0.0, self.t_pk.ptr, self.t_ptr.ptr,
                            self.ksp.ptr, self.C, self.grid.ptr, self.C, self.rowmap.ptr, self.staged_adj, lr, self.nlong,

@@ -102,7 +102,7 @@ def test_fused_long_rows(B, C, runs, monkeypatch):
     A = sense_operator_fused(B, N, coord, maps, 2.0)
     d = A._dev
     assert (d.runs is not None) == runs
-    assert (d.runs[4] if runs else d.nlong) > 0
+    assert (d.runs['nseg'] if runs else d.nlong) > 0
     ref = osense.SenseOperator(N, coord, maps, 2.0)
     x = synth.rand64c(rs, int(np.prod(N)), 1)
     y = synth.rand64c(rs, ref.M * C, 1)
