@@ -110,6 +110,14 @@ int ib200_ccsrmm(void *stream, int adjoint, int exwrite, int64_t m, int64_t k, i
 int ib200_interleave(void *stream, int64_t rows, int64_t ncols, const void *X, int64_t ldx, void *Xil, int64_t pitch);
 int ib200_deinterleave(void *stream, int64_t rows, int64_t ncols, const void *Yil, int64_t pitch,
                        float beta_re, float beta_im, void *Y, int64_t ldy);
+/* Same with a row permutation on the interleaved side: row r of X goes to / comes from row perm[r] of the
+ * interleaved array (fused SENSE recipe: k-space is kept in tile-sorted sample order internally).
+ * ib200_invert_perm writes inv[perm[i]] = i. */
+int ib200_interleave_rows(void *stream, int64_t rows, int64_t ncols, const void *X, int64_t ldx, void *Xil, int64_t pitch,
+                          const int32_t *perm);
+int ib200_deinterleave_rows(void *stream, int64_t rows, int64_t ncols, const void *Yil, int64_t pitch,
+                            float beta_re, float beta_im, void *Y, int64_t ldy, const int32_t *perm);
+int ib200_invert_perm(void *stream, int64_t n, const int32_t *perm, int32_t *inv);
 int ib200_ccsrmm_il(void *stream, int64_t m, int64_t k, int64_t ncols, int64_t nnz, float alpha_re, float alpha_im,
                     const void *vals, const int32_t *colind, const int32_t *rowptr,
                     const void *Xil, int64_t xpitch, void *Yil, int64_t ypitch,
@@ -164,14 +172,15 @@ int ib200_grid_tile_rank(void *stream, const int64_t grid[3], const int64_t tile
  * coordinate; rowweight = optional per-sample weight), the first tap of each axis wrapped into the grid,
  * the tap counts and the output row.  Record r describes sample perm[r] (perm NULL: identity), so the
  * records can be stored in the tile-sorted order ib200_csr_permute_rows produces while results land
- * in the original rows.  *host_flag != 0 on return means some sample needs more than 6 taps on an axis
+ * in the original rows (out_is_record == 0) or in row r itself (out_is_record != 0: k-space kept in the
+ * sorted order between the two gridding steps, so that neighbouring samples are neighbours in memory).  *host_flag != 0 on return means some sample needs more than 6 taps on an axis
  * (or the grid is smaller than the kernel): the caller must stay on the stored-matrix path.
  * Synchronises.  ib200_kb_gather computes Yil[out][c] = alpha * sum_taps w * Xil[tap][c] for ncols
  * interleaved columns (Xil = grid[z][y][x][c] with `xpitch` elements per grid point). */
 int ib200_kb_record_bytes(void);
 int ib200_kb_records(void *stream, int64_t m, const double *coord, const int64_t grid[3], double width,
                      const double *table, int ntable, const float *rowweight, const float *f0, const float *f1,
-                     const float *f2, const int32_t *perm, void *records, int *host_flag);
+                     const float *f2, const int32_t *perm, int out_is_record, void *records, int *host_flag);
 int ib200_kb_gather(void *stream, int64_t m, int64_t ncols, float alpha_re, float alpha_im, const void *records,
                     const void *grid_il, int64_t xpitch, const int64_t grid[3], void *Yil, int64_t ypitch);
 /* x-run form of a stored adjoint in tile-major row order (fused SENSE recipe, csrc/csrmm_runs.cu): the four
@@ -179,14 +188,16 @@ int ib200_kb_gather(void *stream, int64_t m, int64_t ncols, float alpha_re, floa
  * entries, padded to a multiple of four entries.  ib200_csr_runs_count fills run_ptr[kp/4 + 1] and returns
  * the number of run entries, and -- for runs longer than seg_len entries, which are cut into segments
  * of seg_len -- the number of segments and of such runs; ib200_csr_runs_fill writes ids[entries] (int32),
- * w4[entries] (4 floats each), seg_desc[4*segments] and split_desc[4*split runs] (int32 quadruples).
+ * w4[entries] (4 floats each), seg_desc[4*segments] and split_desc[4*split runs] (int32 quadruples);
+ * colmap (optional) renames the columns: ids hold colmap[col] (k-space kept in sorted sample order).
  * ib200_ccsrmm_runs computes Yil[rowmap[r]][c] = alpha * sum_p w(r,p) * Xil[col(r,p)][c] for all kp rows
  * (rowmap < 0: nothing stored) with an even number of interleaved columns; `scratch` holds the partial
  * sums of the segments: segments * 4 * 2*pow2ceil(ncols/2) complex words.  The first two synchronise. */
 int ib200_csr_runs_count(void *stream, int64_t kp, const int32_t *rowptr, const void *packed, int seg_len,
                          int32_t *run_ptr, int64_t *host_entries, int *host_segments, int *host_split);
 int ib200_csr_runs_fill(void *stream, int64_t kp, const int32_t *rowptr, const void *packed, int seg_len,
-                        const int32_t *run_ptr, int32_t *ids, void *w4, int32_t *seg_desc, int32_t *split_desc);
+                        const int32_t *run_ptr, int32_t *ids, void *w4, int32_t *seg_desc, int32_t *split_desc,
+                        const int32_t *colmap);
 int ib200_ccsrmm_runs(void *stream, int64_t kp, int64_t ncols, float alpha_re, float alpha_im, const int32_t *run_ptr,
                       const int32_t *ids, const void *w4, const void *Xil, int64_t xpitch, void *Yil, int64_t ypitch,
                       const int32_t *rowmap, int seg_len, const int32_t *seg_desc, int nseg, const int32_t *split_desc,

@@ -36,6 +36,9 @@ SIGNATURES = {
     "ib200_ccsrmm": (_i, [_vp, _i, _i, _i64, _i64, _i64, _i64, _f, _f, _vp, _vp, _vp, _vp, _i64, _f, _f, _vp, _i64]),
     "ib200_interleave": (_i, [_vp, _i64, _i64, _vp, _i64, _vp, _i64]),
     "ib200_deinterleave": (_i, [_vp, _i64, _i64, _vp, _i64, _f, _f, _vp, _i64]),
+    "ib200_interleave_rows": (_i, [_vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp]),
+    "ib200_deinterleave_rows": (_i, [_vp, _i64, _i64, _vp, _i64, _f, _f, _vp, _i64, _vp]),
+    "ib200_invert_perm": (_i, [_vp, _i64, _vp, _vp]),
     "ib200_ccsrmm_il": (_i, [_vp, _i64, _i64, _i64, _i64, _f, _f, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i,
                              _vp, _i, _i]),
     "ib200_csr_permute_rows": (_i, [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
@@ -44,13 +47,13 @@ SIGNATURES = {
     "ib200_ccsrmm_ilr": (_i, [_vp, _i64, _i64, _i64, _i64, _f, _f, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i,
                               _vp, _i, _i]),
     "ib200_kb_record_bytes": (_i, []),
-    "ib200_kb_records": (_i, [_vp, _i64, _vp, POINTER(_i64), c_double, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp,
+    "ib200_kb_records": (_i, [_vp, _i64, _vp, POINTER(_i64), c_double, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp,
                               POINTER(_i)]),
     "ib200_kb_gather": (_i, [_vp, _i64, _i64, _f, _f, _vp, _vp, _i64, POINTER(_i64), _vp, _i64]),
     "ib200_grid_support_windows": (_i, [_vp, POINTER(_i64), _i64, _vp, _vp, POINTER(_i64), _vp, _vp, POINTER(_i64)]),
     "ib200_sense_plan_set_support": (_i, [_vp, _vp, _i]),
     "ib200_csr_runs_count": (_i, [_vp, _i64, _vp, _vp, _i, _vp, POINTER(_i64), POINTER(_i), POINTER(_i)]),
-    "ib200_csr_runs_fill": (_i, [_vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "ib200_csr_runs_fill": (_i, [_vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ib200_ccsrmm_runs": (_i, [_vp, _i64, _i64, _f, _f, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i, _vp, _i, _vp, _i, _vp]),
     "ib200_grid_tile_rank2": (_i, [_vp, POINTER(_i64), POINTER(_i64), POINTER(_i64), _vp, POINTER(_i64)]),
     "ib200_grid_tile_rank": (_i, [_vp, POINTER(_i64), POINTER(_i64), _vp, _vp, POINTER(_i64)]),

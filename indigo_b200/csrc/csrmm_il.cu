@@ -30,7 +30,8 @@ static const int kTrRows = 64;
 
 template <bool POW2>
 __global__ void __launch_bounds__(256) interleave_kernel(int64_t rows, int C, int log2C, const c64 *__restrict__ X,
-                                                         int64_t ldx, c64 *__restrict__ Xil, int64_t pitch) {
+                                                         int64_t ldx, c64 *__restrict__ Xil, int64_t pitch,
+                                                         const int32_t *__restrict__ perm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c64 *tile = reinterpret_cast<c64 *>(smem_raw);                 // [C][kTrRows + 1]
     const int64_t r0 = (int64_t)blockIdx.x * kTrRows;
@@ -44,7 +45,8 @@ __global__ void __launch_bounds__(256) interleave_kernel(int64_t rows, int C, in
     for (int i = threadIdx.x; i < n; i += 256) {
         const int rr = POW2 ? (i >> log2C) : (i / C);
         const int c = POW2 ? (i & (C - 1)) : (i - rr * C);
-        Xil[(r0 + rr) * pitch + c] = tile[c * (kTrRows + 1) + rr];
+        const int64_t dst = perm ? (int64_t)__ldg(perm + r0 + rr) : r0 + rr;
+        Xil[dst * pitch + c] = tile[c * (kTrRows + 1) + rr];
     }
 }
 
@@ -52,7 +54,8 @@ __global__ void __launch_bounds__(256) interleave_kernel(int64_t rows, int C, in
 template <bool POW2>
 __global__ void __launch_bounds__(256) deinterleave_kernel(int64_t rows, int C, int log2C,
                                                            const c64 *__restrict__ Yil, int64_t pitch, c64 beta,
-                                                           int beta_zero, c64 *__restrict__ Y, int64_t ldy) {
+                                                           int beta_zero, c64 *__restrict__ Y, int64_t ldy,
+                                                           const int32_t *__restrict__ perm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c64 *tile = reinterpret_cast<c64 *>(smem_raw);
     const int64_t r0 = (int64_t)blockIdx.x * kTrRows;
@@ -61,7 +64,8 @@ __global__ void __launch_bounds__(256) deinterleave_kernel(int64_t rows, int C, 
     for (int i = threadIdx.x; i < n; i += 256) {
         const int rr = POW2 ? (i >> log2C) : (i / C);
         const int c = POW2 ? (i & (C - 1)) : (i - rr * C);
-        tile[c * (kTrRows + 1) + rr] = __ldg(Yil + (r0 + rr) * pitch + c);
+        const int64_t src = perm ? (int64_t)__ldg(perm + r0 + rr) : r0 + rr;
+        tile[c * (kTrRows + 1) + rr] = __ldg(Yil + src * pitch + c);
     }
     __syncthreads();
     const int r = threadIdx.x & (kTrRows - 1);
@@ -622,6 +626,11 @@ __global__ void __launch_bounds__(256) tile_rank2_kernel(int n0, int n1, int n2,
     }
 }
 
+__global__ void __launch_bounds__(256) invert_perm_kernel(int64_t n, const int32_t *__restrict__ perm, int32_t *__restrict__ inv) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) inv[perm[i]] = (int32_t)i;
+}
+
 static int pow2_ceil(int64_t v) { int p = 1; while (p < v) p <<= 1; return p; }
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
@@ -635,7 +644,8 @@ using namespace ib200;
 
 extern "C" {
 
-int ib200_interleave(void *stream, int64_t rows, int64_t ncols, const void *X, int64_t ldx, void *Xil, int64_t pitch) {
+static int interleave_impl(void *stream, int64_t rows, int64_t ncols, const void *X, int64_t ldx, void *Xil, int64_t pitch,
+                           const int32_t *perm) {
     IB200_REQUIRE(rows >= 0 && ncols >= 0, "negative dimension");
     if (rows == 0 || ncols == 0) return 0;
     IB200_REQUIRE(X && Xil, "null pointer");
@@ -646,14 +656,23 @@ int ib200_interleave(void *stream, int64_t rows, int64_t ncols, const void *X, i
     const int64_t blocks = ceil_div(rows, kTrRows);
     IB200_REQUIRE(blocks < (1LL << 31), "too many rows for one launch");
     const bool p2 = (C & (C - 1)) == 0;
-    if (p2) interleave_kernel<true><<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(rows, C, ilog2(C), (const c64 *)X, ldx, (c64 *)Xil, pitch);
-    else    interleave_kernel<false><<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(rows, C, 0, (const c64 *)X, ldx, (c64 *)Xil, pitch);
+    if (p2) interleave_kernel<true><<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(rows, C, ilog2(C), (const c64 *)X, ldx, (c64 *)Xil, pitch, perm);
+    else    interleave_kernel<false><<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(rows, C, 0, (const c64 *)X, ldx, (c64 *)Xil, pitch, perm);
     IB200_LAUNCH_CHECK();
     return 0;
 }
 
-int ib200_deinterleave(void *stream, int64_t rows, int64_t ncols, const void *Yil, int64_t pitch, float br, float bi,
-                       void *Y, int64_t ldy) {
+int ib200_interleave(void *stream, int64_t rows, int64_t ncols, const void *X, int64_t ldx, void *Xil, int64_t pitch) {
+    return interleave_impl(stream, rows, ncols, X, ldx, Xil, pitch, nullptr);
+}
+
+int ib200_interleave_rows(void *stream, int64_t rows, int64_t ncols, const void *X, int64_t ldx, void *Xil, int64_t pitch,
+                          const int32_t *perm) {
+    return interleave_impl(stream, rows, ncols, X, ldx, Xil, pitch, perm);
+}
+
+static int deinterleave_impl(void *stream, int64_t rows, int64_t ncols, const void *Yil, int64_t pitch, float br, float bi,
+                             void *Y, int64_t ldy, const int32_t *perm) {
     IB200_REQUIRE(rows >= 0 && ncols >= 0, "negative dimension");
     if (rows == 0 || ncols == 0) return 0;
     IB200_REQUIRE(Y && Yil, "null pointer");
@@ -665,8 +684,27 @@ int ib200_deinterleave(void *stream, int64_t rows, int64_t ncols, const void *Yi
     IB200_REQUIRE(blocks < (1LL << 31), "too many rows for one launch");
     const int b0 = (br == 0.f && bi == 0.f) ? 1 : 0;
     const bool p2 = (C & (C - 1)) == 0;
-    if (p2) deinterleave_kernel<true><<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(rows, C, ilog2(C), (const c64 *)Yil, pitch, mk(br, bi), b0, (c64 *)Y, ldy);
-    else    deinterleave_kernel<false><<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(rows, C, 0, (const c64 *)Yil, pitch, mk(br, bi), b0, (c64 *)Y, ldy);
+    if (p2) deinterleave_kernel<true><<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(rows, C, ilog2(C), (const c64 *)Yil, pitch, mk(br, bi), b0, (c64 *)Y, ldy, perm);
+    else    deinterleave_kernel<false><<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(rows, C, 0, (const c64 *)Yil, pitch, mk(br, bi), b0, (c64 *)Y, ldy, perm);
+    IB200_LAUNCH_CHECK();
+    return 0;
+}
+
+int ib200_deinterleave(void *stream, int64_t rows, int64_t ncols, const void *Yil, int64_t pitch, float br, float bi,
+                       void *Y, int64_t ldy) {
+    return deinterleave_impl(stream, rows, ncols, Yil, pitch, br, bi, Y, ldy, nullptr);
+}
+
+int ib200_deinterleave_rows(void *stream, int64_t rows, int64_t ncols, const void *Yil, int64_t pitch, float br, float bi,
+                            void *Y, int64_t ldy, const int32_t *perm) {
+    return deinterleave_impl(stream, rows, ncols, Yil, pitch, br, bi, Y, ldy, perm);
+}
+
+int ib200_invert_perm(void *stream, int64_t n, const int32_t *perm, int32_t *inv) {
+    IB200_REQUIRE(n >= 0 && n < (1LL << 31), "bad length");
+    if (n == 0) return 0;
+    IB200_REQUIRE(perm && inv, "null pointer");
+    invert_perm_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(n, perm, inv);
     IB200_LAUNCH_CHECK();
     return 0;
 }

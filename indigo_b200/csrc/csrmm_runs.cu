@@ -24,12 +24,13 @@ namespace ib200 {
 
 static const int kRun = 4;            // grid points per run = x extent of the adjoint's tiles
 static const int kRunPad = 4;         // run lists are padded to multiples of this many entries
+static const int kRunAhead = 4;       // batches between the L1 prefetch of a batch and its use
 
 struct __align__(8) RunPacked { int32_t col; float w; };
 
 // number of distinct samples in the four rows of run r (rows hold ascending sample indices)
 __device__ __forceinline__ int run_merge(const int32_t *__restrict__ rowptr, const RunPacked *__restrict__ ent, int64_t r,
-                                         int32_t *ids, float4 *w4) {
+                                         int32_t *ids, float4 *w4, const int32_t *__restrict__ colmap = nullptr) {
     int p[kRun], e[kRun];
 #pragma unroll
     for (int i = 0; i < kRun; ++i) { p[i] = rowptr[kRun * r + i]; e[i] = rowptr[kRun * r + i + 1]; }
@@ -46,7 +47,7 @@ __device__ __forceinline__ int run_merge(const int32_t *__restrict__ rowptr, con
             w[i] = 0.f;
             if (p[i] < e[i] && ent[p[i]].col == m) { w[i] = ent[p[i]].w; ++p[i]; }
         }
-        if (ids) { ids[n] = m; w4[n] = make_float4(w[0], w[1], w[2], w[3]); }
+        if (ids) { ids[n] = colmap ? colmap[m] : m; w4[n] = make_float4(w[0], w[1], w[2], w[3]); }
         ++n;
     }
     return n;
@@ -69,11 +70,12 @@ __global__ void __launch_bounds__(128) run_fill_kernel(int64_t nruns, const int3
                                                        const RunPacked *__restrict__ ent, int seg_len,
                                                        const int32_t *__restrict__ run_ptr, int32_t *__restrict__ ids,
                                                        float4 *__restrict__ w4, int4 *__restrict__ seg_desc,
-                                                       int4 *__restrict__ split_desc, int *cursors) {
+                                                       int4 *__restrict__ split_desc, int *cursors,
+                                                       const int32_t *__restrict__ colmap) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nruns) return;
     const int a = run_ptr[r], b = run_ptr[r + 1];
-    const int n = run_merge(rowptr, ent, r, ids + a, w4 + a);
+    const int n = run_merge(rowptr, ent, r, ids + a, w4 + a, colmap);
     for (int q = a + n; q < b; ++q) { ids[q] = n ? ids[a + n - 1] : 0; w4[q] = make_float4(0.f, 0.f, 0.f, 0.f); }
     if (b - a > seg_len) {
         const int k = (b - a + seg_len - 1) / seg_len;
@@ -91,9 +93,9 @@ __global__ void __launch_bounds__(128) run_fill_kernel(int64_t nruns, const int3
 struct RunBatch { int4 id; float4 w[kRunPad]; };
 
 __device__ __forceinline__ void run_load_batch(RunBatch &e, const int32_t *__restrict__ ids, const float4 *__restrict__ w4, int p) {
-    e.id = __ldcs(reinterpret_cast<const int4 *>(ids + p));
+    e.id = __ldg(reinterpret_cast<const int4 *>(ids + p));
 #pragma unroll
-    for (int u = 0; u < kRunPad; ++u) e.w[u] = __ldcs(w4 + p + u);
+    for (int u = 0; u < kRunPad; ++u) e.w[u] = __ldg(w4 + p + u);
 }
 
 // acc[t][0..1] += sum over the run entries [a, b) of w_t * X[id]  (two coils per lane, b - a a multiple of 4)
@@ -110,6 +112,10 @@ __device__ __forceinline__ void run_walk(int a, int b, const int32_t *__restrict
         RunBatch nx;
         const bool more = p + kRunPad < b;
         if (more) run_load_batch(nx, ids, w4, p + kRunPad);
+        if (p + kRunAhead * kRunPad < b) {                           // pull a later batch into L1 (64 + 16 bytes)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(w4 + p + kRunAhead * kRunPad));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(ids + p + kRunAhead * kRunPad));
+        }
 #pragma unroll
         for (int u = 0; u < kRunPad; ++u) {
             const pk2 x0 = p_make(x[u].x, x[u].y), x1 = p_make(x[u].z, x[u].w);
@@ -277,7 +283,8 @@ int ib200_csr_runs_count(void *stream, int64_t kp, const int32_t *rowptr, const 
 }
 
 int ib200_csr_runs_fill(void *stream, int64_t kp, const int32_t *rowptr, const void *packed, int seg_len,
-                        const int32_t *run_ptr, int32_t *ids, void *w4, int32_t *seg_desc, int32_t *split_desc) {
+                        const int32_t *run_ptr, int32_t *ids, void *w4, int32_t *seg_desc, int32_t *split_desc,
+                        const int32_t *colmap) {
     IB200_REQUIRE(kp >= 0 && kp % kRun == 0 && kp < (1LL << 31), "row count must be a multiple of 4");
     IB200_REQUIRE(seg_len >= kRunPad && seg_len % kRunPad == 0, "segment length must be a positive multiple of 4");
     if (kp == 0) return 0;
@@ -291,7 +298,7 @@ int ib200_csr_runs_fill(void *stream, int64_t kp, const int32_t *rowptr, const v
     cudaMemsetAsync(cursors, 0, 2 * sizeof(int), s);
     run_fill_kernel<<<(unsigned)ceil_div(nruns, 128), 128, 0, s>>>(nruns, rowptr, (const RunPacked *)packed, seg_len, run_ptr,
                                                                   ids, (float4 *)w4, (int4 *)seg_desc, (int4 *)split_desc,
-                                                                  cursors);
+                                                                  cursors, colmap);
     count_launch();
     cudaError_t e = cudaStreamSynchronize(s);
     cudaFree(cursors);

@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(128) kb_records_kernel(int64_t m, const double
                                                          int ntab, const float *__restrict__ rowweight,
                                                          const float *__restrict__ f0, const float *__restrict__ f1,
                                                          const float *__restrict__ f2,
-                                                         const int32_t *__restrict__ perm,
+                                                         const int32_t *__restrict__ perm, int out_is_record,
                                                          KbRecord *__restrict__ rec, int *flag) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= m) return;
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(128) kb_records_kernel(int64_t m, const double
         for (int t = 0; t < kKbTaps; ++t) q.wz[t] = __fmul_rn(rw, q.wz[t]);
     }
     q.ix0 = first[0]; q.iy0 = first[1]; q.iz0 = first[2];
-    q.out = (int32_t)i;
+    q.out = out_is_record ? (int32_t)r : (int32_t)i;
     q.ntaps = cnt[0] | (cnt[1] << 8) | (cnt[2] << 16);
     q.pad = 0;
     rec[r] = q;
@@ -312,7 +312,7 @@ int ib200_kb_record_bytes(void) { return (int)sizeof(KbRecord); }
 
 int ib200_kb_records(void *stream, int64_t m, const double *coord, const int64_t grid[3], double width,
                      const double *table, int ntable, const float *rowweight, const float *f0, const float *f1,
-                     const float *f2, const int32_t *perm, void *records, int *host_flag) {
+                     const float *f2, const int32_t *perm, int out_is_record, void *records, int *host_flag) {
     IB200_REQUIRE(m >= 0 && grid && host_flag, "bad arguments");
     *host_flag = 0;
     if (m == 0) return 0;
@@ -326,7 +326,7 @@ int ib200_kb_records(void *stream, int64_t m, const double *coord, const int64_t
     IB200_TRY(cudaMalloc(&flag, sizeof(int)));
     cudaMemsetAsync(flag, 0, sizeof(int), s);
     kb_records_kernel<<<(unsigned)ceil_div(m, 128), 128, 0, s>>>(m, coord, (int)grid[0], (int)grid[1], (int)grid[2], width,
-                                                                table, ntable, rowweight, f0, f1, f2, perm,
+                                                                table, ntable, rowweight, f0, f1, f2, perm, out_is_record,
                                                                 (KbRecord *)records, flag);
     count_launch();
     cudaMemcpyAsync(host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, s);

@@ -39,6 +39,7 @@ class SenseDevice(object):
     staged_fwd = -41
     staged_adj = -4
     allow_separable = True     # forward gridding from 96-byte separable-weight records instead of stored entries
+    allow_sorted_ksp = True    # keep k-space in tile-sorted sample order between the two gridding steps
     allow_runs = True          # adjoint gridding on merged x-runs of the stored adjoint (csrc/csrmm_runs.cu)
     run_long_thresh = 1024     # runs with more entries than this are cut into segments of this length
     allow_windows = True       # k-space support windows: skip the grid outside the trajectory's support
@@ -93,7 +94,7 @@ class SenseDevice(object):
         del colrank, work
         # real-weight packed entries (8 B instead of 12 B per stored entry, half the multiplies) when
         # the centring phase folded into G' is real, i.e. on every grid the fused path serves
-        self.real, self.kb = False, None
+        self.real, self.kb, self.ksp_sorted, self.pos = False, None, False, None
         if self.nnz and self.allow_real:
             pk = np.dtype('int64')                                     # 8-byte (int32 column, float32 weight) records
             g_pk = B.zero_array((self.nnz + 2,), pk, name='G.packed')  # +2: the staged kernel copies 16-byte granules
@@ -121,9 +122,20 @@ class SenseDevice(object):
                 del rank8, junk
                 # separable Kaiser-Bessel records in the same tile-sorted order: the forward gather then
                 # needs no stored entries at all (csrc/kbgrid.cu)
+                # k-space between the two gridding steps is kept in this sorted order when both the separable
+                # forward gather and the x-run adjoint gather serve it: samples that are neighbours on the grid
+                # are then neighbours in memory (the original spoke order scatters them over 0.9 GB at cfg3)
                 self.kb = None
+                use_runs = self.allow_runs and C % 2 == 0 and self.tile[0] == 4 and kp % 4 == 0
+                self.ksp_sorted = bool(self.allow_separable and use_runs and self.allow_sorted_ksp)
                 if self.allow_separable:
-                    self.kb = kb_records_device(B, self.oN, coord, beta, weights, width, n, perm=self.g_map)
+                    self.kb = kb_records_device(B, self.oN, coord, beta, weights, width, n, perm=self.g_map,
+                                                out_sorted=self.ksp_sorted)
+                if self.kb is None:
+                    self.ksp_sorted = False
+                if self.ksp_sorted:
+                    self.pos = B.empty_array((max(self.M, 1),), i32, name='G.sorted.position')
+                    lib.invert_perm(s, self.M, self.g_map.ptr, self.pos.ptr)
                 if self.kb is not None:
                     self.g_pk = self.g_ptr = None
             del g_pk
@@ -169,7 +181,8 @@ class SenseDevice(object):
             w4 = B.empty_array((4 * ne,), np.dtype('float32'), name='G.H.runs.w4')
             segd = B.empty_array((4 * max(nsg, 1),), i32, name='G.H.runs.segments')
             spld = B.empty_array((4 * max(nsp, 1),), i32, name='G.H.runs.split')
-            lib.csr_runs_fill(s, kp, self.t_ptr.ptr, self.t_pk.ptr, seg, run_ptr.ptr, ids.ptr, w4.ptr, segd.ptr, spld.ptr)
+            lib.csr_runs_fill(s, kp, self.t_ptr.ptr, self.t_pk.ptr, seg, run_ptr.ptr, ids.ptr, w4.ptr, segd.ptr, spld.ptr,
+                              self.pos.ptr if self.ksp_sorted else None)
             cl = 1
             while cl < C // 2:
                 cl *= 2
@@ -257,9 +270,15 @@ def make_fused_classes(ops):
             if forward:
                 d.expand_fft(x)
                 d.grid_to_samples(alpha)
-                lib.deinterleave(s, d.M, d.C, d.ksp.ptr, d.C, b.real, b.imag, y.ptr, d.M)
+                if d.ksp_sorted:
+                    lib.deinterleave_rows(s, d.M, d.C, d.ksp.ptr, d.C, b.real, b.imag, y.ptr, d.M, d.pos.ptr)
+                else:
+                    lib.deinterleave(s, d.M, d.C, d.ksp.ptr, d.C, b.real, b.imag, y.ptr, d.M)
             else:
-                lib.interleave(s, d.M, d.C, x.ptr, d.M, d.ksp.ptr, d.C)
+                if d.ksp_sorted:
+                    lib.interleave_rows(s, d.M, d.C, x.ptr, d.M, d.ksp.ptr, d.C, d.pos.ptr)
+                else:
+                    lib.interleave(s, d.M, d.C, x.ptr, d.M, d.ksp.ptr, d.C)
                 d.samples_to_grid()
                 d.ifft_combine(y, alpha, beta)
 

@@ -168,9 +168,10 @@ def _fftc_axis_factors(oN):
     return out
 
 
-def kb_records_device(B, oN, coord, beta, weights=None, width=3, n=128, perm=None):
+def kb_records_device(B, oN, coord, beta, weights=None, width=3, n=128, perm=None, out_sorted=False):
     """Separable-weight records of G' = interp*mod*scale (ib200_kb_records, csrc/kbgrid.cu): 96 bytes per
-    sample instead of a stored row.  perm (device int32, optional): record r describes sample perm[r].
+    sample instead of a stored row.  perm (device int32, optional): record r describes sample perm[r];
+    out_sorted: results go to row r (sorted order) instead of row perm[r].
     Returns the device array of records, or None when this grid / kernel width is not served
     (complex centring phase, more than 6 taps per axis)."""
     import ctypes
@@ -194,7 +195,7 @@ def kb_records_device(B, oN, coord, beta, weights=None, width=3, n=128, perm=Non
     grid = (ctypes.c_int64 * 3)(*oN)
     lib.kb_records(s, m, coord_d.ptr, grid, float(width), table_d.ptr, int(table.size),
                    w_d.ptr if w_d is not None else None, f_d[0].ptr, f_d[1].ptr, f_d[2].ptr,
-                   perm.ptr if perm is not None else None, rec.ptr, ctypes.byref(flag))
+                   perm.ptr if perm is not None else None, 1 if out_sorted else 0, rec.ptr, ctypes.byref(flag))
     return rec if flag.value == 0 else None
 
 
