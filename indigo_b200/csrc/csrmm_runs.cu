@@ -24,7 +24,6 @@ namespace ib200 {
 
 static const int kRun = 4;            // grid points per run = x extent of the adjoint's tiles
 static const int kRunPad = 4;         // run lists are padded to multiples of this many entries
-static const int kRunAhead = 4;       // batches between the L1 prefetch of a batch and its use
 
 struct __align__(8) RunPacked { int32_t col; float w; };
 
@@ -90,51 +89,71 @@ __global__ void __launch_bounds__(128) run_fill_kernel(int64_t nruns, const int3
 }
 
 // ---------------------------------------------------------------------------------------------------
-struct RunBatch { int4 id; float4 w[kRunPad]; };
+// Run entries reach the lane group through a small ring in shared memory that cp.async fills kRingDepth
+// batches ahead (a batch = 4 ids + 4 x 4 weights = 80 bytes): the stream of entries costs no registers
+// while it is in flight, and by the time a batch is needed it is a shared-memory read instead of an
+// L2/DRAM round trip in front of the dependent gathers (ncu: 22 % of the stall samples sat on the first
+// use of a register-prefetched batch, profiles/r01_s7_*).
+static const int kRingDepth = 4;
+static const int kBatchBytes = 16 + 16 * kRunPad;
 
-__device__ __forceinline__ void run_load_batch(RunBatch &e, const int32_t *__restrict__ ids, const float4 *__restrict__ w4, int p) {
-    e.id = __ldg(reinterpret_cast<const int4 *>(ids + p));
-#pragma unroll
-    for (int u = 0; u < kRunPad; ++u) e.w[u] = __ldg(w4 + p + u);
+__device__ __forceinline__ void run_issue_batch(unsigned char *slot, const int32_t *__restrict__ ids,
+                                                const float4 *__restrict__ w4, int p, int gl, int CL) {
+    for (int ch = gl; ch < 1 + kRunPad; ch += CL) {
+        const void *src = ch == 0 ? (const void *)(ids + p) : (const void *)(w4 + p + ch - 1);
+        const unsigned d = (unsigned)__cvta_generic_to_shared(slot + 16 * ch);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
+    }
 }
 
 // acc[t][0..1] += sum over the run entries [a, b) of w_t * X[id]  (two coils per lane, b - a a multiple of 4)
+// ring: kRingDepth * kBatchBytes bytes of shared memory owned by this lane group; gmask: its lanes.
 __device__ __forceinline__ void run_walk(int a, int b, const int32_t *__restrict__ ids, const float4 *__restrict__ w4,
-                                         const char *xb, uint32_t xpitch_bytes, pk2 (&acc)[kRun][2]) {
-    RunBatch e;
-    run_load_batch(e, ids, w4, a);
-    for (int p = a; p < b; p += kRunPad) {
+                                         const char *xb, uint32_t xpitch_bytes, pk2 (&acc)[kRun][2],
+                                         unsigned char *ring, int gl, int CL, unsigned gmask) {
+    const int nb = (b - a) / kRunPad;
+#pragma unroll
+    for (int k = 0; k < kRingDepth; ++k) {
+        if (k < nb) run_issue_batch(ring + k * kBatchBytes, ids, w4, a + k * kRunPad, gl, CL);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    }
+    int slot = 0;
+    for (int k = 0; k < nb; ++k) {
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(kRingDepth - 1) : "memory");
+        __syncwarp(gmask);
+        const unsigned char *sl = ring + slot * kBatchBytes;
+        const int4 id = *reinterpret_cast<const int4 *>(sl);
+        float4 w[kRunPad];
+#pragma unroll
+        for (int u = 0; u < kRunPad; ++u) w[u] = *reinterpret_cast<const float4 *>(sl + 16 + 16 * u);
         float4 x[kRunPad];
-        const int idv[kRunPad] = {e.id.x, e.id.y, e.id.z, e.id.w};
+        const int idv[kRunPad] = {id.x, id.y, id.z, id.w};
 #pragma unroll
         for (int u = 0; u < kRunPad; ++u)
             x[u] = __ldg(reinterpret_cast<const float4 *>(xb + (uint64_t)(uint32_t)idv[u] * xpitch_bytes));
-        RunBatch nx;
-        const bool more = p + kRunPad < b;
-        if (more) run_load_batch(nx, ids, w4, p + kRunPad);
-        if (p + kRunAhead * kRunPad < b) {                           // pull a later batch into L1 (64 + 16 bytes)
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(w4 + p + kRunAhead * kRunPad));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(ids + p + kRunAhead * kRunPad));
-        }
+        __syncwarp(gmask);                                           // every lane has read the slot
+        if (k + kRingDepth < nb) run_issue_batch(ring + slot * kBatchBytes, ids, w4, a + (k + kRingDepth) * kRunPad, gl, CL);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
 #pragma unroll
         for (int u = 0; u < kRunPad; ++u) {
             const pk2 x0 = p_make(x[u].x, x[u].y), x1 = p_make(x[u].z, x[u].w);
-            const float wv[kRun] = {e.w[u].x, e.w[u].y, e.w[u].z, e.w[u].w};
+            const float wv[kRun] = {w[u].x, w[u].y, w[u].z, w[u].w};
 #pragma unroll
             for (int t = 0; t < kRun; ++t) {
                 acc[t][0] = p_fma(p_bc(wv[t]), x0, acc[t][0]);
                 acc[t][1] = p_fma(p_bc(wv[t]), x1, acc[t][1]);
             }
         }
-        if (more) e = nx;
+        if (++slot == kRingDepth) slot = 0;
     }
 }
 
-__device__ __forceinline__ void run_store(const pk2 (&acc)[kRun][2], c64 alpha, const int32_t *__restrict__ rowmap,
-                                          int64_t run, c64 *__restrict__ Yil, int64_t ypitch, int coil) {
+__device__ __forceinline__ void run_store(const pk2 (&acc)[kRun][2], c64 alpha, int4 rows, c64 *__restrict__ Yil,
+                                          int64_t ypitch, int coil) {
+    const int rv[kRun] = {rows.x, rows.y, rows.z, rows.w};
 #pragma unroll
     for (int t = 0; t < kRun; ++t) {
-        const int64_t out = (int64_t)__ldg(rowmap + kRun * run + t);
+        const int64_t out = (int64_t)rv[t];
         if (out >= 0) {
             const c64 o0 = cmul(alpha, mk(p_lo(acc[t][0]), p_hi(acc[t][0])));
             const c64 o1 = cmul(alpha, mk(p_lo(acc[t][1]), p_hi(acc[t][1])));
@@ -173,16 +192,20 @@ __global__ void __launch_bounds__(256) csrmm_runs_kernel(int64_t nruns, int C, c
         for (int q = e0 + 32 * (int)threadIdx.x; q < e1; q += 32 * 256)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(ids + q));
     }
+    extern __shared__ __align__(16) unsigned char ring_all[];
+    unsigned char *ring = ring_all + (size_t)group * (kRingDepth * kBatchBytes);
+    const unsigned gmask = CL >= 32 ? 0xffffffffu : (((1u << CL) - 1u) << (((int)(threadIdx.x & 31) / CL) * CL));
     for (int i = 0; i < rpg; ++i) {
         const int64_t run = run0 + (int64_t)i * GPB;
         if (run >= nruns) break;
         const int a = __ldg(run_ptr + run), b = __ldg(run_ptr + run + 1);
         if (b - a > seg_len) continue;
+        const int4 rows = __ldg(reinterpret_cast<const int4 *>(rowmap + kRun * run));   // needed last, loaded first
         pk2 acc[kRun][2];
 #pragma unroll
         for (int t = 0; t < kRun; ++t) { acc[t][0] = p_make(0.f, 0.f); acc[t][1] = p_make(0.f, 0.f); }
-        if (a < b) run_walk(a, b, ids, w4, xb, xpitch_bytes, acc);
-        if (coil_ok) run_store(acc, alpha, rowmap, run, Yil, ypitch, coil);
+        if (a < b) run_walk(a, b, ids, w4, xb, xpitch_bytes, acc, ring, gl, CL, gmask);
+        if (coil_ok) run_store(acc, alpha, rows, Yil, ypitch, coil);
     }
 }
 
@@ -199,10 +222,13 @@ __global__ void __launch_bounds__(256) csrmm_runs_seg_kernel(int nseg, int C, co
     if (sidx >= nseg) return;
     const int4 d = __ldg(seg_desc + sidx);
     const char *xb = reinterpret_cast<const char *>(Xil + (coil < C ? coil : 0));
+    extern __shared__ __align__(16) unsigned char ring_all[];
+    unsigned char *ring = ring_all + (size_t)group * (kRingDepth * kBatchBytes);
+    const unsigned gmask = CL >= 32 ? 0xffffffffu : (((1u << CL) - 1u) << (((int)(threadIdx.x & 31) / CL) * CL));
     pk2 acc[kRun][2];
 #pragma unroll
     for (int t = 0; t < kRun; ++t) { acc[t][0] = p_make(0.f, 0.f); acc[t][1] = p_make(0.f, 0.f); }
-    run_walk(d.y, d.z, ids, w4, xb, xpitch_bytes, acc);
+    run_walk(d.y, d.z, ids, w4, xb, xpitch_bytes, acc, ring, gl, CL, gmask);
     if (coil < C) {
 #pragma unroll
         for (int t = 0; t < kRun; ++t)
@@ -234,7 +260,7 @@ __global__ void __launch_bounds__(256) csrmm_runs_fold_kernel(int nsplit, int C,
             acc[t][1] = p_add(acc[t][1], p_make(v.z, v.w));
         }
     }
-    run_store(acc, alpha, rowmap, d.x, Yil, ypitch, coil);
+    run_store(acc, alpha, __ldg(reinterpret_cast<const int4 *>(rowmap + kRun * (int64_t)d.x)), Yil, ypitch, coil);
 }
 
 int exclusive_scan_public(cudaStream_t s, int64_t n, const int32_t *in, int32_t *out);   // csrmm.cu
@@ -329,16 +355,21 @@ int ib200_ccsrmm_runs(void *stream, int64_t kp, int64_t ncols, float ar, float a
     const int64_t blocks = ceil_div(nruns, (int64_t)GPB * rpg);
     IB200_REQUIRE(blocks < (1LL << 31), "too many runs for one launch");
     const int cpitch = 2 * CL;                                       // scratch row: 2*CL complex words per point
+    const size_t ring_bytes = (size_t)GPB * kRingDepth * kBatchBytes;
     const uint32_t pb = (uint32_t)(xpitch * sizeof(c64));
 #define IB200_RUNS_CASE(cl)                                                                                            \
     case cl:                                                                                                           \
+        if (ring_bytes > 48 * 1024) {                                                                                  \
+            IB200_TRY(cudaFuncSetAttribute(csrmm_runs_kernel<cl>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes)); \
+            IB200_TRY(cudaFuncSetAttribute(csrmm_runs_seg_kernel<cl>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes)); \
+        }                                                                                                              \
         if (nseg > 0) {                                                                                                \
-            csrmm_runs_seg_kernel<cl><<<(unsigned)ceil_div(nseg, GPB), 256, 0, s>>>(nseg, (int)ncols, (const int4 *)seg_desc, ids, \
+            csrmm_runs_seg_kernel<cl><<<(unsigned)ceil_div(nseg, GPB), 256, ring_bytes, s>>>(nseg, (int)ncols, (const int4 *)seg_desc, ids, \
                                                                                    (const float4 *)w4, (const c64 *)Xil, pb,  \
                                                                                    (c64 *)scratch, cpitch);           \
             count_launch();                                                                                            \
         }                                                                                                              \
-        csrmm_runs_kernel<cl><<<(unsigned)blocks, 256, 0, s>>>(nruns, (int)ncols, alpha, run_ptr, ids, (const float4 *)w4, \
+        csrmm_runs_kernel<cl><<<(unsigned)blocks, 256, ring_bytes, s>>>(nruns, (int)ncols, alpha, run_ptr, ids, (const float4 *)w4, \
                                                                (const c64 *)Xil, pb, (c64 *)Yil, ypitch, rowmap, seg_len, rpg); \
         if (nsplit > 0) {                                                                                              \
             count_launch();                                                                                            \
