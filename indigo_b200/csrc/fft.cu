@@ -68,10 +68,22 @@ static int launch_spec(cudaStream_t s, const FftKernelArgs &k) {
     return launch_spec_t<N, R0, R1, R2, AXIS0, 256>(s, k);
 }
 
+static int try_pk_pass(cudaStream_t s, const IlPassArgs &a, int n, const FftStages &st, bool swap_in, bool swap_out);
+
 // returns 1 if a specialised kernel was launched, 0 if none applies, <0 / >0 on error (offset by 1000)
 static int try_spec(cudaStream_t s, bool axis0, const FftKernelArgs &k) {
     if (!axis0 && k.inner < kSpecL) return 0;
     if (axis0 && k.outer < kSpecL) return 0;
+    // strided axes transformed in place, no fused diagonal, whole 16-line tiles: the packed two-lines-per-thread
+    // passes of the fused recipe (fft_pk.cuh) serve Backend.fftn / ifftn too
+    if (!axis0 && k.x == k.y && !k.din && !k.dout && k.inner % kSpecL == 0 && k.inner < (1LL << 32) &&
+        !(k.swap_in && k.swap_out) && k.in0 == 0 && k.in1 == k.n && k.out0 == 0 && k.out1 == k.n) {
+        IlPassArgs a;
+        a.x = k.y; a.tw = k.tw; a.inner = k.inner; a.outer = k.outer; a.outer_stride = k.outer_stride;
+        a.pstride = (unsigned)k.inner; a.in0 = 0; a.in1 = k.n; a.out0 = 0; a.out1 = k.n;
+        const int r = try_pk_pass(s, a, k.n, k.st, k.swap_in != 0, k.swap_out != 0);
+        if (r != 0) return r;
+    }
 #define IB200_TRY_SPEC(n, r0, r1, r2)                                                        \
     if (fft_spec_matches(k, n, r0, r1, r2)) {                                                \
         const int rc = axis0 ? launch_spec<n, r0, r1, r2, true>(s, k) : launch_spec<n, r0, r1, r2, false>(s, k); \

@@ -23,8 +23,8 @@ int64_t smem_optin() { return 232448; }
 
 using namespace ib200;
 
-extern "C" const char *emul_last_error() { return g_err; }
 static int g_pk_used = 0;
+extern "C" const char *emul_last_error() { return g_err; }
 extern "C" int emul_pk_used() { const int v = g_pk_used; g_pk_used = 0; return v; }
 
 extern "C" int emul_fft(int ndim, const int64_t *dims, int64_t batch, float *y, const float *x, int direction,
@@ -43,6 +43,37 @@ extern "C" int emul_fft(int ndim, const int64_t *dims, int64_t batch, float *y, 
         if (tile_L_out) tile_L_out[pass] = k.L;
         ++pass;
         bool spec = false;
+        // same routing as try_spec (fft.cu): in-place strided passes over whole tiles use the packed bodies
+        if (use_spec && !axis0 && k.inner >= kSpecL && k.x == k.y && !k.din && !k.dout && k.inner % kSpecL == 0 &&
+            !(k.swap_in && k.swap_out) && getenv("IB200_FFT_NOPK") == nullptr && (k.outer_stride & 1) == 0 &&
+            ((uintptr_t)k.y & 15) == 0) {
+            IlPassArgs a;
+            a.x = k.y; a.tw = k.tw; a.inner = k.inner; a.outer = k.outer; a.outer_stride = k.outer_stride;
+            a.pstride = (unsigned)k.inner; a.in0 = 0; a.in1 = k.n; a.out0 = 0; a.out1 = k.n;
+#define EMUL_PKI(n, r0, r1, r2)                                                                    \
+            if (!spec && fft_spec_matches(k, n, r0, r1, r2)) {                                     \
+                spec = true; ++g_pk_used;                                                          \
+                std::vector<float> sp(2 * pk_buf_floats(n) + 4);                                   \
+                std::vector<c64> raw((size_t)n * kSpecL + 2);                                      \
+                const bool pkp = getenv("IB200_FFT_NOPKP") == nullptr && pkp_mid_pairs(n, r1, r2, 256) <= 16; \
+                const int64_t nb = (k.inner / kSpecL) * k.outer;                                   \
+                for (int64_t b = 0; b < nb; ++b) {                                                 \
+                    if (pkp) {                                                                     \
+                        pkp_prefetch(a, b, raw.data(), 0, 1);                                      \
+                        if (k.swap_in)       fft_pkp_tile_body<n, r0, r1, r2, true, false, 0>(a, b, -1, sp.data(), raw.data(), 0, 1); \
+                        else if (k.swap_out) fft_pkp_tile_body<n, r0, r1, r2, false, true, 0>(a, b, -1, sp.data(), raw.data(), 0, 1); \
+                        else                 fft_pkp_tile_body<n, r0, r1, r2, false, false, 0>(a, b, -1, sp.data(), raw.data(), 0, 1); \
+                    } else {                                                                       \
+                        if (k.swap_in)       fft_pk_pass_body<n, r0, r1, r2, true, false, 0>(a, sp.data(), b, 0, 1);  \
+                        else if (k.swap_out) fft_pk_pass_body<n, r0, r1, r2, false, true, 0>(a, sp.data(), b, 0, 1);  \
+                        else                 fft_pk_pass_body<n, r0, r1, r2, false, false, 0>(a, sp.data(), b, 0, 1); \
+                    }                                                                              \
+                }                                                                                  \
+            }
+            IB200_FFT_SPEC_LIST(EMUL_PKI)
+#undef EMUL_PKI
+            if (spec) { if (tile_L_out) tile_L_out[pass - 1] = -16; return 0; }
+        }
         if (use_spec && (axis0 ? k.outer >= kSpecL : k.inner >= kSpecL)) {
 #define EMUL_SPEC(n, r0, r1, r2)                                                                   \
             if (!spec && fft_spec_matches(k, n, r0, r1, r2)) {                                     \

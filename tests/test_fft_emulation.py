@@ -40,7 +40,9 @@ def rel(a, b):
 
 SHAPES = [(2, 3), (3, 2), (5, 2), (7, 2), (11, 1), (13, 2), (16, 2), (22, 4), (23, 2), (24, 3), (25, 2), (128, 2),
           (416, 2), (512, 1), (17 * 4, 2), (289, 1), (24, 22, 3), (23, 24, 25, 2), (16, 13, 7, 3), (416, 4, 3, 2),
-          (3, 5, 416, 1), (1, 24, 2), (24, 1, 2), (1, 1, 3), (34, 38, 2, 3)]
+          (3, 5, 416, 1), (1, 24, 2), (24, 1, 2), (1, 1, 3), (34, 38, 2, 3),
+          # strided axes with whole 16-line tiles and a specialised length: packed two-line passes (fft_pk.cuh)
+          (32, 64, 2), (16, 416, 1), (32, 32, 52, 2), (16, 208, 32, 1), (48, 128, 2)]
 
 
 @pytest.mark.parametrize("shape", SHAPES)
