@@ -139,7 +139,7 @@ class CallTimer(object):
 
     def __init__(self, B, torch, dev=None):
         self.B, self.torch, self.records, self.on = B, torch, [], False
-        for name in ("ccsrmm", "fftn", "ifftn"):
+        for name in ("ccsrmm", "ccsrmm_packed", "fftn", "ifftn"):
             setattr(B, name, self._wrap(name, getattr(B, name)))
         if dev is not None:
             fft = dict(op="fused_fft", N=dev.N, oN=dev.oN, C=dev.C)
@@ -171,7 +171,13 @@ class CallTimer(object):
             e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
             n0 = self.B._lib.launch_count()
             e0.record(); out = fn(*a, **k); e1.record()
-            if name == "ccsrmm":
+            if name == "ccsrmm_packed":
+                y, shp, nnz, _, _, x = a[:6]
+                beta = k.get("beta", a[7] if len(a) > 7 else 0)
+                info = dict(op="ccsrmm", m=int(shp[0]), k=int(shp[1]), nnz=int(nnz), ncols=int(x.shape[1]),
+                            adjoint=False, beta_nz=bool(beta != 0))
+                key = "ccsrmm[packed real A %dx%d nnz/row=%.0f ncols=%d]" % (shp[0], shp[1], nnz / max(1, shp[0]), x.shape[1])
+            elif name == "ccsrmm":
                 y, shp, ind, ptr, vals, x = a[:6]
                 adj = k.get("adjoint", a[8] if len(a) > 8 else False)
                 beta = k.get("beta", a[7] if len(a) > 7 else 0)

@@ -221,6 +221,66 @@ def make_backend_class(Base, name="B200Backend"):
                 self._adj = (t_ptr, t_ind, t_val)
             return self._adj
 
+        # -- multi-column products of real-valued matrices ------------------------------
+        # Gridding matrices are real on the grids MRI uses (the centring phase is +-1).  For them the
+        # interleaved gather runs on packed (int32 column, float weight) entries staged through shared
+        # memory (ib200_ccsrmm_ilr, 8 bytes per entry instead of 12, half the multiplies), and rows
+        # longer than `long_thresh` entries get a whole CTA each.  Decided once per matrix.
+        long_thresh = 512
+
+        def _packed(self, which):
+            """{'pk', 'ptr', 'long', 'nlong'} for which = 'fwd' (this matrix) or 'adj' (stored adjoint), or None
+            when the values are not real / the matrix is empty."""
+            cache = self.__dict__.setdefault('_pk_cache', {})
+            if which in cache:
+                return cache[which]
+            b = self._backend
+            if which == 'fwd':
+                rows, ptr, ind, val = self.shape[0], self.rowPtrs, self.colInds, self.values
+            else:
+                rows = self.shape[1]
+                ptr, ind, val = self._stored_adjoint()
+            nnz = int(self.values.size)
+            info = None
+            if nnz > 0 and rows > 0 and b.packed_real:
+                pk = b.zero_array((nnz + 2,), np.dtype('int64'), name=self._name + ".packed." + which)
+                hmax = (ctypes.c_float * 2)()
+                b._lib.csr_pack_real(b._stream, nnz, val.ptr, ind.ptr, pk.ptr, hmax)
+                if hmax[1] <= 1e-8 * hmax[0]:
+                    cnt = ctypes.c_int()
+                    b._lib.csr_long_rows(b._stream, rows, ptr.ptr, self.long_thresh, None, 0, ctypes.byref(cnt))
+                    nlong, lr = int(cnt.value), None
+                    if nlong:
+                        lr = b.empty_array((nlong,), np.dtype('int32'), name=self._name + ".longrows." + which)
+                        b._lib.csr_long_rows(b._stream, rows, ptr.ptr, self.long_thresh, lr.ptr, nlong, ctypes.byref(cnt))
+                    info = dict(pk=pk, ptr=ptr, long=lr, nlong=nlong)
+            cache[which] = info
+            return info
+
+        def _packed_product(self, which, y, x, alpha, beta):
+            """Y = alpha * op(A) X + beta * Y through the packed real-weight gather; False when not applicable."""
+            b = self._backend
+            ncols = int(x.shape[1]) if x.ndim == 2 else 1
+            m, k = self.shape if which == 'fwd' else self.shape[::-1]
+            nnz = int(self.values.size)
+            (ar, ai), (br, bi) = _re_im(alpha), _re_im(beta)
+            if not (2 <= ncols <= 32 and m > 0 and k > 0 and nnz * ncols >= b.il_min_work and (ar != 0.0 or ai != 0.0)):
+                return False
+            info = self._packed(which)
+            if info is None:
+                return False
+            b.ccsrmm_packed(y, (m, k), nnz, info, self.long_thresh, x, alpha, beta)
+            return True
+
+        def forward(self, y, x, alpha=1, beta=0):
+            assert x.dtype == _C64, "Bad dtype: expected compelx64, got %s" % x.dtype
+            assert y.dtype == _C64, "Bad dtype: expected compelx64, got %s" % y.dtype
+            assert self.values.dtype == _C64
+            if self._packed_product('fwd', y, x, alpha, beta):
+                return
+            self._backend.ccsrmm(y, self.shape, self.colInds, self.rowPtrs, self.values, x, alpha=alpha, beta=beta,
+                                 adjoint=False, exwrite=True)
+
         def adjoint(self, y, x, alpha=1, beta=0):
             assert x.dtype == _C64, "Bad dtype: expected compelx64, got %s" % x.dtype
             assert y.dtype == _C64, "Bad dtype: expected compelx64, got %s" % y.dtype
@@ -229,6 +289,8 @@ def make_backend_class(Base, name="B200Backend"):
             if self._exwrite or not self._use_stored_adjoint():
                 return b.ccsrmm(y, self.shape, self.colInds, self.rowPtrs, self.values, x,
                                 alpha=alpha, beta=beta, adjoint=True, exwrite=self._exwrite)
+            if self._packed_product('adj', y, x, alpha, beta):
+                return
             t_ptr, t_ind, t_val = self._stored_adjoint()
             b.ccsrmm(y, self.shape[::-1], t_ind, t_ptr, t_val, x, alpha=alpha, beta=beta, adjoint=False, exwrite=True)
 
@@ -237,6 +299,7 @@ def make_backend_class(Base, name="B200Backend"):
         csr_matrix = B200Csr
         stored_adjoints = 'auto'        # True / False / 'auto': keep A^H in CSR for non-exclusive-write matrices
         il_min_work = 1 << 14           # nnz*ncols from which multi-column products take the interleaved path
+        packed_real = True              # real-valued matrices: packed 8-byte entries for multi-column products
 
         def __init__(self, device_id=0, lib=None):
             super().__init__(device_id)
@@ -382,6 +445,19 @@ def make_backend_class(Base, name="B200Backend"):
             self._lib.ccsrmm(self._stream, 1 if adjoint else 0, 1 if exwrite else 0, m, k, ncols,
                              nnz, ar, ai, A_vals.ptr, A_indx.ptr, A_ptr.ptr, x.ptr, x.ld,
                              br, bi, y.ptr, y.ld)
+
+        def ccsrmm_packed(self, y, A_shape, nnz, info, long_thresh, x, alpha=1, beta=0):
+            """Y = alpha*A*X + beta*Y for a real-valued A held as packed (int32 column, float weight) entries
+            (B200Csr._packed): interleave -> staged packed gather (+ one CTA per long row) -> deinterleave."""
+            (ar, ai), (br, bi) = _re_im(alpha), _re_im(beta)
+            m, k = (int(v) for v in A_shape)
+            ncols, s = int(x.shape[1]), self._stream
+            xil = self._il_scratch('x', k * ncols)
+            yil = self._il_scratch('y', m * ncols)
+            self._lib.interleave(s, k, ncols, x.ptr, x.ld, xil, ncols)
+            self._lib.ccsrmm_ilr(s, m, k, ncols, nnz, ar, ai, info['pk'].ptr, info['ptr'].ptr, xil, ncols, yil, ncols,
+                                 None, -4, info['long'].ptr if info['nlong'] else None, info['nlong'], long_thresh)
+            self._lib.deinterleave(s, m, ncols, yil, ncols, br, bi, y.ptr, y.ld)
 
         def cdiamm(self, y, shape, offsets, data, x, alpha=1.0, beta=0.0, adjoint=True):
             (ar, ai), (br, bi) = _re_im(alpha), _re_im(beta)

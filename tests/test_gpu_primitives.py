@@ -142,6 +142,32 @@ def _rand_csr(rs, m, n, density):
     return A
 
 
+@pytest.mark.parametrize("Kc", [2, 3, 8, 16, 17, 32])
+@pytest.mark.parametrize("alpha,beta", [(1, 0), (0.5 - 2j, 1.5)])
+def test_csr_matrix_real_values_packed(B, Kc, alpha, beta, monkeypatch):
+    """Real-valued matrices (gridding matrices on MRI grids) take the packed 8-byte-entry gather for
+    multi-column products, forward and through the stored adjoint, with long rows split off."""
+    monkeypatch.setattr(B, "il_min_work", 0)
+    monkeypatch.setattr(B.csr_matrix, "long_thresh", 16)
+    rs = np.random.RandomState(77 + Kc)
+    M, N = 300, 211
+    A = spp.random(M, N, density=0.08, format='csr', random_state=rs, dtype=np.float32).tolil()
+    A[5, :] = rs.rand(N).astype(np.float32)                  # a long row and (transposed) a long column
+    A[:, 7] = rs.rand(M, 1).astype(np.float32)
+    A = A.tocsr().astype(C64); A.sort_indices()
+    Ad = B.csr_matrix(B, A)
+    x, y0 = synth.rand64c(rs, N, Kc), synth.rand64c(rs, M, Kc)
+    yd = B.copy_array(y0)
+    Ad.forward(yd, B.copy_array(x), alpha=alpha, beta=beta)
+    assert Ad._packed('fwd') is not None and Ad._packed('fwd')['nlong'] > 0
+    np.testing.assert_allclose(yd.to_host(), alpha * (A @ x) + beta * y0, atol=2e-4, rtol=1e-5)
+    x, y0 = synth.rand64c(rs, M, Kc), synth.rand64c(rs, N, Kc)
+    yd = B.copy_array(y0)
+    Ad.adjoint(yd, B.copy_array(x), alpha=alpha, beta=beta)
+    assert Ad._packed('adj') is not None and Ad._packed('adj')['nlong'] > 0
+    np.testing.assert_allclose(yd.to_host(), alpha * (A.conj().T @ x) + beta * y0, atol=2e-4, rtol=1e-5)
+
+
 @pytest.mark.parametrize("M,N,Kc,density", list(product([23, 45], [45, 23], [1, 8, 9, 17], [0.01, 0.1, 0.5])))
 def test_csr_matrix(B, M, N, Kc, density, il):
     rs = np.random.RandomState(M * N + Kc)
