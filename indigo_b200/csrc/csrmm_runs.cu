@@ -106,15 +106,17 @@ __device__ __forceinline__ void run_issue_batch(unsigned char *slot, const int32
     }
 }
 
-// acc[t][0..1] += sum over the run entries [a, b) of w_t * X[id]  (two coils per lane, b - a a multiple of 4)
-// ring: kRingDepth * kBatchBytes bytes of shared memory owned by this lane group; gmask: its lanes.
+// acc[t][0..1] += sum over the run entries [a, b) of w_(p0+t) * X[id]  (two coils per lane, PPL of the run's four
+// points per lane starting at p0, b - a a multiple of 4).  ring: kRingDepth * kBatchBytes bytes of shared memory
+// owned by this lane group of GS lanes (gl = lane within the group); gmask: its lanes.
+template <int PPL>
 __device__ __forceinline__ void run_walk(int a, int b, const int32_t *__restrict__ ids, const float4 *__restrict__ w4,
-                                         const char *xb, uint32_t xpitch_bytes, pk2 (&acc)[kRun][2],
-                                         unsigned char *ring, int gl, int CL, unsigned gmask) {
+                                         const char *xb, uint32_t xpitch_bytes, pk2 (&acc)[PPL][2],
+                                         unsigned char *ring, int gl, int GS, int p0, unsigned gmask) {
     const int nb = (b - a) / kRunPad;
 #pragma unroll
     for (int k = 0; k < kRingDepth; ++k) {
-        if (k < nb) run_issue_batch(ring + k * kBatchBytes, ids, w4, a + k * kRunPad, gl, CL);
+        if (k < nb) run_issue_batch(ring + k * kBatchBytes, ids, w4, a + k * kRunPad, gl, GS);
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     }
     int slot = 0;
@@ -123,36 +125,49 @@ __device__ __forceinline__ void run_walk(int a, int b, const int32_t *__restrict
         __syncwarp(gmask);
         const unsigned char *sl = ring + slot * kBatchBytes;
         const int4 id = *reinterpret_cast<const int4 *>(sl);
-        float4 w[kRunPad];
+        float w[kRunPad][PPL];
 #pragma unroll
-        for (int u = 0; u < kRunPad; ++u) w[u] = *reinterpret_cast<const float4 *>(sl + 16 + 16 * u);
+        for (int u = 0; u < kRunPad; ++u) {
+            const unsigned char *wp = sl + 16 + 16 * u + 4 * p0;
+            if (PPL == 4) { const float4 v = *reinterpret_cast<const float4 *>(wp); w[u][0] = v.x; w[u][1 % PPL] = v.y; w[u][2 % PPL] = v.z; w[u][3 % PPL] = v.w; }
+            else if (PPL == 2) { const float2 v = *reinterpret_cast<const float2 *>(wp); w[u][0] = v.x; w[u][1 % PPL] = v.y; }
+            else w[u][0] = *reinterpret_cast<const float *>(wp);
+        }
         float4 x[kRunPad];
         const int idv[kRunPad] = {id.x, id.y, id.z, id.w};
 #pragma unroll
         for (int u = 0; u < kRunPad; ++u)
             x[u] = __ldg(reinterpret_cast<const float4 *>(xb + (uint64_t)(uint32_t)idv[u] * xpitch_bytes));
         __syncwarp(gmask);                                           // every lane has read the slot
-        if (k + kRingDepth < nb) run_issue_batch(ring + slot * kBatchBytes, ids, w4, a + (k + kRingDepth) * kRunPad, gl, CL);
+        if (k + kRingDepth < nb) run_issue_batch(ring + slot * kBatchBytes, ids, w4, a + (k + kRingDepth) * kRunPad, gl, GS);
         asm volatile("cp.async.commit_group;\n" ::: "memory");
 #pragma unroll
         for (int u = 0; u < kRunPad; ++u) {
             const pk2 x0 = p_make(x[u].x, x[u].y), x1 = p_make(x[u].z, x[u].w);
-            const float wv[kRun] = {w[u].x, w[u].y, w[u].z, w[u].w};
 #pragma unroll
-            for (int t = 0; t < kRun; ++t) {
-                acc[t][0] = p_fma(p_bc(wv[t]), x0, acc[t][0]);
-                acc[t][1] = p_fma(p_bc(wv[t]), x1, acc[t][1]);
+            for (int t = 0; t < PPL; ++t) {
+                acc[t][0] = p_fma(p_bc(w[u][t]), x0, acc[t][0]);
+                acc[t][1] = p_fma(p_bc(w[u][t]), x1, acc[t][1]);
             }
         }
         if (++slot == kRingDepth) slot = 0;
     }
 }
 
-__device__ __forceinline__ void run_store(const pk2 (&acc)[kRun][2], c64 alpha, int4 rows, c64 *__restrict__ Yil,
-                                          int64_t ypitch, int coil) {
-    const int rv[kRun] = {rows.x, rows.y, rows.z, rows.w};
+// output rows of this lane's points: needed last, loaded first (one 4/8/16-byte load)
+template <int PPL>
+__device__ __forceinline__ void run_rows(const int32_t *__restrict__ rowmap, int64_t run, int p0, int (&rv)[PPL]) {
+    const int32_t *p = rowmap + kRun * run + p0;
+    if (PPL == 4) { const int4 v = __ldg(reinterpret_cast<const int4 *>(p)); rv[0] = v.x; rv[1 % PPL] = v.y; rv[2 % PPL] = v.z; rv[3 % PPL] = v.w; }
+    else if (PPL == 2) { const int2 v = __ldg(reinterpret_cast<const int2 *>(p)); rv[0] = v.x; rv[1 % PPL] = v.y; }
+    else rv[0] = __ldg(p);
+}
+
+template <int PPL>
+__device__ __forceinline__ void run_store(const pk2 (&acc)[PPL][2], c64 alpha, const int (&rv)[PPL],
+                                          c64 *__restrict__ Yil, int64_t ypitch, int coil) {
 #pragma unroll
-    for (int t = 0; t < kRun; ++t) {
+    for (int t = 0; t < PPL; ++t) {
         const int64_t out = (int64_t)rv[t];
         if (out >= 0) {
             const c64 o0 = cmul(alpha, mk(p_lo(acc[t][0]), p_hi(acc[t][0])));
@@ -162,28 +177,44 @@ __device__ __forceinline__ void run_store(const pk2 (&acc)[kRun][2], c64 alpha, 
     }
 }
 
+// lane geometry shared by the three kernels: a group of GS = CL*PL lanes serves one run; lane (cl, pl) of
+// the group holds coils 2*cl, 2*cl+1 of the points pl*PPL .. pl*PPL + PPL-1 (PPL = 4/PL).  PL > 1 is used
+// when there are fewer than 8 coils (coil-sharded operators): the lanes a wide coil vector would fill
+// are spent on the four points of the run instead, so that a warp still serves 8 runs, not 32.
+template <int CL, int PL>
+struct RunLanes {
+    static constexpr int GS = CL * PL, GPB = 256 / GS, PPL = kRun / PL;
+    int gl, group, coil, p0;
+    unsigned gmask;
+    unsigned char *ring;
+    __device__ __forceinline__ RunLanes(unsigned char *ring_all) {
+        gl = (int)(threadIdx.x & (GS - 1)); group = (int)(threadIdx.x / GS);
+        coil = 2 * (gl & (CL - 1)); p0 = (gl / CL) * PPL;
+        gmask = GS >= 32 ? 0xffffffffu : (((1u << GS) - 1u) << (((int)(threadIdx.x & 31) / GS) * GS));
+        ring = ring_all + (size_t)group * (kRingDepth * kBatchBytes);
+    }
+};
+
 // Yil[rowmap[4*run + i]][c] = alpha * sum_e w_i(e) * Xil[id(e)][c]        (rowmap < 0: nothing stored)
-// CL lanes per run, two coils per lane (one 16-byte gather per run entry and lane).  Runs longer than
-// seg_len are left to the segment kernels below.
-template <int CL>
+// Runs longer than seg_len are left to the segment kernels below.
+template <int CL, int PL>
 __global__ void __launch_bounds__(256) csrmm_runs_kernel(int64_t nruns, int C, c64 alpha,
                                                          const int32_t *__restrict__ run_ptr,
                                                          const int32_t *__restrict__ ids, const float4 *__restrict__ w4,
                                                          const c64 *__restrict__ Xil, uint32_t xpitch_bytes,
                                                          c64 *__restrict__ Yil, int64_t ypitch,
                                                          const int32_t *__restrict__ rowmap, int seg_len, int rpg) {
-    constexpr int GPB = 256 / CL;
-    const int gl = (int)(threadIdx.x & (CL - 1)), group = (int)(threadIdx.x / CL);
-    const int coil = 2 * gl;
-    const bool coil_ok = coil < C;
-    const char *xb = reinterpret_cast<const char *>(Xil + (coil_ok ? coil : 0));
-    const int64_t run0 = (int64_t)blockIdx.x * ((int64_t)GPB * rpg) + group;
+    extern __shared__ __align__(16) unsigned char ring_all[];
+    using L = RunLanes<CL, PL>;
+    const L ln(ring_all);
+    const bool coil_ok = ln.coil < C;
+    const char *xb = reinterpret_cast<const char *>(Xil + (coil_ok ? ln.coil : 0));
+    const int64_t run0 = (int64_t)blockIdx.x * ((int64_t)L::GPB * rpg) + ln.group;
     {
-        // The run lists of this CTA are one contiguous range that is read exactly once, a batch at a time
-        // with one batch of look-ahead: pull the whole range into L2 up front so that the batch loads pay
-        // an L2 hit instead of a DRAM round trip each.
-        const int64_t first = (int64_t)blockIdx.x * ((int64_t)GPB * rpg);
-        const int64_t last = first + (int64_t)GPB * rpg < nruns ? first + (int64_t)GPB * rpg : nruns;
+        // The run lists of this CTA are one contiguous range that is read exactly once: pull it into L2 up
+        // front so that the ring's cp.async batches pay an L2 hit instead of a DRAM round trip each.
+        const int64_t first = (int64_t)blockIdx.x * ((int64_t)L::GPB * rpg);
+        const int64_t last = first + (int64_t)L::GPB * rpg < nruns ? first + (int64_t)L::GPB * rpg : nruns;
         const int e0 = __ldg(run_ptr + first);
         int e1 = __ldg(run_ptr + last);
         if (e1 - e0 > 64 * 1024) e1 = e0 + 64 * 1024;                // split runs: their segments prefetch for themselves
@@ -192,75 +223,71 @@ __global__ void __launch_bounds__(256) csrmm_runs_kernel(int64_t nruns, int C, c
         for (int q = e0 + 32 * (int)threadIdx.x; q < e1; q += 32 * 256)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(ids + q));
     }
-    extern __shared__ __align__(16) unsigned char ring_all[];
-    unsigned char *ring = ring_all + (size_t)group * (kRingDepth * kBatchBytes);
-    const unsigned gmask = CL >= 32 ? 0xffffffffu : (((1u << CL) - 1u) << (((int)(threadIdx.x & 31) / CL) * CL));
     for (int i = 0; i < rpg; ++i) {
-        const int64_t run = run0 + (int64_t)i * GPB;
+        const int64_t run = run0 + (int64_t)i * L::GPB;
         if (run >= nruns) break;
         const int a = __ldg(run_ptr + run), b = __ldg(run_ptr + run + 1);
         if (b - a > seg_len) continue;
-        const int4 rows = __ldg(reinterpret_cast<const int4 *>(rowmap + kRun * run));   // needed last, loaded first
-        pk2 acc[kRun][2];
+        int rv[L::PPL];
+        run_rows<L::PPL>(rowmap, run, ln.p0, rv);
+        pk2 acc[L::PPL][2];
 #pragma unroll
-        for (int t = 0; t < kRun; ++t) { acc[t][0] = p_make(0.f, 0.f); acc[t][1] = p_make(0.f, 0.f); }
-        if (a < b) run_walk(a, b, ids, w4, xb, xpitch_bytes, acc, ring, gl, CL, gmask);
-        if (coil_ok) run_store(acc, alpha, rows, Yil, ypitch, coil);
+        for (int t = 0; t < L::PPL; ++t) { acc[t][0] = p_make(0.f, 0.f); acc[t][1] = p_make(0.f, 0.f); }
+        if (a < b) run_walk<L::PPL>(a, b, ids, w4, xb, xpitch_bytes, acc, ln.ring, ln.gl, L::GS, ln.p0, ln.gmask);
+        if (coil_ok) run_store<L::PPL>(acc, alpha, rv, Yil, ypitch, ln.coil);
     }
 }
 
 // one lane group per segment of a split run: partial sums into scratch[seg][t][coil]
-template <int CL>
+template <int CL, int PL>
 __global__ void __launch_bounds__(256) csrmm_runs_seg_kernel(int nseg, int C, const int4 *__restrict__ seg_desc,
                                                              const int32_t *__restrict__ ids,
                                                              const float4 *__restrict__ w4, const c64 *__restrict__ Xil,
                                                              uint32_t xpitch_bytes, c64 *__restrict__ scratch, int cpitch) {
-    constexpr int GPB = 256 / CL;
-    const int gl = (int)(threadIdx.x & (CL - 1)), group = (int)(threadIdx.x / CL);
-    const int coil = 2 * gl;
-    const int sidx = blockIdx.x * GPB + group;
+    extern __shared__ __align__(16) unsigned char ring_all[];
+    using L = RunLanes<CL, PL>;
+    const L ln(ring_all);
+    const int sidx = blockIdx.x * L::GPB + ln.group;
     if (sidx >= nseg) return;
     const int4 d = __ldg(seg_desc + sidx);
-    const char *xb = reinterpret_cast<const char *>(Xil + (coil < C ? coil : 0));
-    extern __shared__ __align__(16) unsigned char ring_all[];
-    unsigned char *ring = ring_all + (size_t)group * (kRingDepth * kBatchBytes);
-    const unsigned gmask = CL >= 32 ? 0xffffffffu : (((1u << CL) - 1u) << (((int)(threadIdx.x & 31) / CL) * CL));
-    pk2 acc[kRun][2];
+    const char *xb = reinterpret_cast<const char *>(Xil + (ln.coil < C ? ln.coil : 0));
+    pk2 acc[L::PPL][2];
 #pragma unroll
-    for (int t = 0; t < kRun; ++t) { acc[t][0] = p_make(0.f, 0.f); acc[t][1] = p_make(0.f, 0.f); }
-    run_walk(d.y, d.z, ids, w4, xb, xpitch_bytes, acc, ring, gl, CL, gmask);
-    if (coil < C) {
+    for (int t = 0; t < L::PPL; ++t) { acc[t][0] = p_make(0.f, 0.f); acc[t][1] = p_make(0.f, 0.f); }
+    run_walk<L::PPL>(d.y, d.z, ids, w4, xb, xpitch_bytes, acc, ln.ring, ln.gl, L::GS, ln.p0, ln.gmask);
+    if (ln.coil < C) {
 #pragma unroll
-        for (int t = 0; t < kRun; ++t)
-            *reinterpret_cast<float4 *>(scratch + ((int64_t)sidx * kRun + t) * cpitch + coil) =
+        for (int t = 0; t < L::PPL; ++t)
+            *reinterpret_cast<float4 *>(scratch + ((int64_t)sidx * kRun + ln.p0 + t) * cpitch + ln.coil) =
                 make_float4(p_lo(acc[t][0]), p_hi(acc[t][0]), p_lo(acc[t][1]), p_hi(acc[t][1]));
     }
 }
 
 // one lane group per split run: partial sums added in segment order, then stored like any other run
-template <int CL>
+template <int CL, int PL>
 __global__ void __launch_bounds__(256) csrmm_runs_fold_kernel(int nsplit, int C, c64 alpha, const int4 *__restrict__ split_desc,
                                                               const c64 *__restrict__ scratch, int cpitch,
                                                               c64 *__restrict__ Yil, int64_t ypitch,
                                                               const int32_t *__restrict__ rowmap) {
-    constexpr int GPB = 256 / CL;
-    const int gl = (int)(threadIdx.x & (CL - 1)), group = (int)(threadIdx.x / CL);
-    const int coil = 2 * gl;
-    const int idx = blockIdx.x * GPB + group;
-    if (idx >= nsplit || coil >= C) return;
+    using L = RunLanes<CL, PL>;
+    const L ln(nullptr);
+    const int idx = blockIdx.x * L::GPB + ln.group;
+    if (idx >= nsplit || ln.coil >= C) return;
     const int4 d = __ldg(split_desc + idx);
-    pk2 acc[kRun][2];
+    pk2 acc[L::PPL][2];
 #pragma unroll
-    for (int t = 0; t < kRun; ++t) { acc[t][0] = p_make(0.f, 0.f); acc[t][1] = p_make(0.f, 0.f); }
+    for (int t = 0; t < L::PPL; ++t) { acc[t][0] = p_make(0.f, 0.f); acc[t][1] = p_make(0.f, 0.f); }
     for (int sgm = d.y; sgm < d.y + d.z; ++sgm) {
 #pragma unroll
-        for (int t = 0; t < kRun; ++t) {
-            const float4 v = *reinterpret_cast<const float4 *>(scratch + ((int64_t)sgm * kRun + t) * cpitch + coil);
+        for (int t = 0; t < L::PPL; ++t) {
+            const float4 v = *reinterpret_cast<const float4 *>(scratch + ((int64_t)sgm * kRun + ln.p0 + t) * cpitch + ln.coil);
             acc[t][0] = p_add(acc[t][0], p_make(v.x, v.y));
             acc[t][1] = p_add(acc[t][1], p_make(v.z, v.w));
         }
     }
-    run_store(acc, alpha, __ldg(reinterpret_cast<const int4 *>(rowmap + kRun * (int64_t)d.x)), Yil, ypitch, coil);
+    int rv[L::PPL];
+    run_rows<L::PPL>(rowmap, d.x, ln.p0, rv);
+    run_store<L::PPL>(acc, alpha, rv, Yil, ypitch, ln.coil);
 }
 
 int exclusive_scan_public(cudaStream_t s, int64_t n, const int32_t *in, int32_t *out);   // csrmm.cu
@@ -350,37 +377,39 @@ int ib200_ccsrmm_runs(void *stream, int64_t kp, int64_t ncols, float ar, float a
     const c64 alpha = mk(ar, ai);
     cudaStream_t s = as_stream(stream);
     const int CL = runs_pow2_ceil(ncols / 2);
+    const int PL = CL >= 4 ? 1 : kRun / CL;                         // lanes of a group split the run's points when coils are few
     const int rpg = 4;
-    const int GPB = 256 / CL;
+    const int GPB = 256 / (CL * PL);
     const int64_t blocks = ceil_div(nruns, (int64_t)GPB * rpg);
     IB200_REQUIRE(blocks < (1LL << 31), "too many runs for one launch");
     const int cpitch = 2 * CL;                                       // scratch row: 2*CL complex words per point
     const size_t ring_bytes = (size_t)GPB * kRingDepth * kBatchBytes;
     const uint32_t pb = (uint32_t)(xpitch * sizeof(c64));
-#define IB200_RUNS_CASE(cl)                                                                                            \
-    case cl:                                                                                                           \
+#define IB200_RUNS_CASE(cl, pl)                                                                                        \
+    case (cl) * 8 + (pl):                                                                                              \
         if (ring_bytes > 48 * 1024) {                                                                                  \
-            IB200_TRY(cudaFuncSetAttribute(csrmm_runs_kernel<cl>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes)); \
-            IB200_TRY(cudaFuncSetAttribute(csrmm_runs_seg_kernel<cl>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes)); \
+            IB200_TRY(cudaFuncSetAttribute(csrmm_runs_kernel<cl, pl>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes)); \
+            IB200_TRY(cudaFuncSetAttribute(csrmm_runs_seg_kernel<cl, pl>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes)); \
         }                                                                                                              \
         if (nseg > 0) {                                                                                                \
-            csrmm_runs_seg_kernel<cl><<<(unsigned)ceil_div(nseg, GPB), 256, ring_bytes, s>>>(nseg, (int)ncols, (const int4 *)seg_desc, ids, \
+            csrmm_runs_seg_kernel<cl, pl><<<(unsigned)ceil_div(nseg, GPB), 256, ring_bytes, s>>>(nseg, (int)ncols, (const int4 *)seg_desc, ids, \
                                                                                    (const float4 *)w4, (const c64 *)Xil, pb,  \
                                                                                    (c64 *)scratch, cpitch);           \
             count_launch();                                                                                            \
         }                                                                                                              \
-        csrmm_runs_kernel<cl><<<(unsigned)blocks, 256, ring_bytes, s>>>(nruns, (int)ncols, alpha, run_ptr, ids, (const float4 *)w4, \
+        csrmm_runs_kernel<cl, pl><<<(unsigned)blocks, 256, ring_bytes, s>>>(nruns, (int)ncols, alpha, run_ptr, ids, (const float4 *)w4, \
                                                                (const c64 *)Xil, pb, (c64 *)Yil, ypitch, rowmap, seg_len, rpg); \
         if (nsplit > 0) {                                                                                              \
             count_launch();                                                                                            \
-            csrmm_runs_fold_kernel<cl><<<(unsigned)ceil_div(nsplit, GPB), 256, 0, s>>>(nsplit, (int)ncols, alpha,      \
+            csrmm_runs_fold_kernel<cl, pl><<<(unsigned)ceil_div(nsplit, GPB), 256, 0, s>>>(nsplit, (int)ncols, alpha,  \
                                                                                       (const int4 *)split_desc, (const c64 *)scratch, \
                                                                                       cpitch, (c64 *)Yil, ypitch, rowmap); \
         }                                                                                                              \
         break
-    switch (CL) {
-        IB200_RUNS_CASE(1); IB200_RUNS_CASE(2); IB200_RUNS_CASE(4); IB200_RUNS_CASE(8); IB200_RUNS_CASE(16); IB200_RUNS_CASE(32);
-        default: set_error("internal: no run gather for CL=%d", CL); return IB200_E_UNSUPPORTED;
+    switch (CL * 8 + PL) {
+        IB200_RUNS_CASE(1, 4); IB200_RUNS_CASE(2, 2); IB200_RUNS_CASE(4, 1); IB200_RUNS_CASE(8, 1); IB200_RUNS_CASE(16, 1);
+        IB200_RUNS_CASE(32, 1);
+        default: set_error("internal: no run gather for CL=%d PL=%d", CL, PL); return IB200_E_UNSUPPORTED;
     }
 #undef IB200_RUNS_CASE
     IB200_LAUNCH_CHECK();
