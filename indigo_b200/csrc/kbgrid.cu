@@ -133,7 +133,7 @@ __device__ __forceinline__ void kb_row(const char *rp, const uint32_t (&xo)[kKbT
 // over the samples of the warp (5 taps per axis except for samples that sit exactly on a grid
 // line, whose sixth tap has weight zero), so control flow is warp-uniform.
 template <int CL, int VC>
-__global__ void __launch_bounds__(256, 3) kb_gather_kernel(int64_t m, int C, c64 alpha, const KbRecord *__restrict__ rec,
+__global__ void __launch_bounds__(256, 4) kb_gather_kernel(int64_t m, int C, c64 alpha, const KbRecord *__restrict__ rec,
                                                            const c64 *__restrict__ grid, uint32_t pitch, int n0, int n1,
                                                            int n2, c64 *__restrict__ Y, int64_t ypitch, int iters) {
     constexpr int SPW = 32 / CL;
