@@ -297,6 +297,43 @@ def run_ours(args):
         b.record()
     sync_all()
     e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_ev)
+    e2e_path = "pinned host -> cudaMemcpyAsync -> AHA.eval -> cudaMemcpyAsync -> pinned host"
+    # ---- end to end, zero-copy: the operator is evaluated on device-mapped views of the same pinned host
+    # buffers (B.mapped_array): the image crosses PCIe inside the first fused pass' load and the result inside
+    # the last pass' store, every step, instead of through separate copies
+    e2e_alt = None
+    try:
+        x_m = B.mapped_array(x_h)
+        y_m = B.mapped_array(y_h) if team is None else None
+
+        def apply_mapped():
+            if team is None:
+                AHA.eval(y_m, x_m)
+            else:
+                AHA.eval(y_d, x_m)
+                team.allreduce_array(y_d)
+                y_d.copy_to(y_h)
+
+        y_ref = np.array(y_h)                                   # result of the copy path, same input
+        apply_mapped(); sync_all()
+        err = float(np.linalg.norm(np.asarray(y_h) - y_ref) / max(np.linalg.norm(y_ref), 1e-30))
+        if err > 1e-6:
+            raise RuntimeError("mapped path deviates from the copy path: %.3e" % err)
+        m_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        sync_all()
+        for a, b in m_ev:
+            a.record(); apply_mapped(); b.record()
+            if team is None:
+                b.synchronize()                                 # the result is in host memory before the next step starts
+        sync_all()
+        m_ms = sum(a.elapsed_time(b) for a, b in m_ev)
+        e2e_alt = {"copy_path_ms_per_step": e2e_ms / args.steps, "mapped_path_ms_per_step": m_ms / args.steps}
+        if m_ms < e2e_ms:
+            e2e_ms = m_ms
+            e2e_path = ("AHA.eval on device-mapped views of the pinned host buffers (B.mapped_array): H2D inside the first "
+                        "pass' load, D2H inside the last pass' store" + ("" if team is None else "; result via all-reduce + copy"))
+    except Exception as exc:                                    # keep the copy path's number
+        e2e_alt = {"mapped_path_error": str(exc)[:200]}
     clk = clocks.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([total_ms, e2e_ms, float(launches)], dtype=torch.float64, device="cuda")
@@ -321,7 +358,8 @@ def run_ours(args):
                        "l2": "no explicit flush: every call streams operands far larger than L2 (grid %.1f GB)" %
                              (8.0 * np.prod([int(n * wl["oversamp"]) for n in N]) * C / world / 1e9)},
             "e2e": {"value": args.steps / (e2e_ms * 1e-3), "unit": "applies/s",
-                    "h2d_bytes_per_step": int(x_h.nbytes), "d2h_bytes_per_step": int(y_h.nbytes)},
+                    "h2d_bytes_per_step": int(x_h.nbytes), "d2h_bytes_per_step": int(y_h.nbytes),
+                    "path": e2e_path, "paths_timed": e2e_alt},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom["call"], "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
                          "frac": dom["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,

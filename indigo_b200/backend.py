@@ -336,6 +336,19 @@ def make_backend_class(Base, name="B200Backend"):
             out._b200_keep = t
             return out
 
+        def mapped_array(self, pinned):
+            """Device-addressable view of a page-locked host array from `pinned_array` (no copy): under unified
+            virtual addressing the kernels read / write the host buffer over PCIe directly, so that an operator
+            evaluated on such views moves its input and output inside its first and last kernel instead of
+            through separate copies.  Only for arrays that are touched once per evaluation (operator inputs and
+            outputs); everything else belongs in HBM."""
+            if not self._pinned(pinned):
+                raise ValueError("mapped_array needs an array from pinned_array()")
+            if not pinned.flags['F_CONTIGUOUS']:
+                raise ValueError("mapped_array needs a column-major array")
+            return self.dndarray(self, pinned.shape, pinned.dtype, own=False,
+                                 data=DevPtr(pinned.ctypes.data, keep=pinned), name='mapped')
+
         def barrier(self):
             self._lib.stream_sync(self._stream)
 
