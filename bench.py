@@ -351,8 +351,8 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "complex64 (fp32 accumulate)",
             "data": "synthetic (seeded kooshball trajectory, rand64c image and unit-RSS coil maps)",
             "config": {"workload": wl["desc"],
-                       "tree": ("fused B200 recipe: expand+FFT (pruned, coil-interleaved) -> G' gather -> stored G'^H gather -> "
-                                "IFFT+combine; 4 fused steps replace the six calls of the -O3 tree" if tree == "fused" else
+                       "tree": ("fused B200 recipe: expand+FFT (pruned, coil-interleaved, support windows) -> separable G' gather -> "
+                                "x-run G'^H gather -> IFFT+combine; 4 fused steps replace the six calls of the -O3 tree" if tree == "fused" else
                                 "-O3 (examples/pics.py recipe), device-built CSR operands, six Backend calls"),
                        "parallelism": "coil-sharded x%d, NCCL all-reduce of the image" % world if world > 1 else "single GPU",
                        "l2": "no explicit flush: every call streams operands far larger than L2 (grid %.1f GB)" %

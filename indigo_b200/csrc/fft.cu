@@ -208,15 +208,19 @@ __global__ void __launch_bounds__(kPkThreads, 2) fft_pkp_pass_kernel(const IlPas
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *bufA = reinterpret_cast<float *>(smem_raw);
     c64 *raw = reinterpret_cast<c64 *>(bufA + pk_buf_floats(N));
+    // twiddle table in shared memory: every butterfly of every tile reads R-1 entries; as cached global loads
+    // they were 15 % of the pass (long-scoreboard stalls on top of the L1 traffic), as shared-memory reads 0
+    c64 *stw = raw + (size_t)N * kSpecL;
     const int tid = (int)threadIdx.x;
     int64_t tile = pkp_next_active(a, blockIdx.x, gridDim.x, ntiles, tid, kPkThreads);
     if (tile < 0) return;
     pkp_prefetch(a, tile, raw, tid, kPkThreads);
+    for (int i = tid; i < N; i += kPkThreads) stw[i] = a.tw[i];
     while (tile >= 0) {
         const int64_t next = pkp_next_active(a, tile + gridDim.x, gridDim.x, ntiles, tid, kPkThreads);
         pkp_wait();
         __syncthreads();                                             // raw[] of this tile visible; bufA of the last tile consumed
-        fft_pkp_tile_body<N, R0, R1, R2, SI, SO, kPkThreads>(a, tile, next, bufA, raw, tid, kPkThreads);
+        fft_pkp_tile_body<N, R0, R1, R2, SI, SO, kPkThreads>(a, tile, next, bufA, raw, tid, kPkThreads, stw);
         tile = next;
     }
 }
@@ -224,7 +228,7 @@ __global__ void __launch_bounds__(kPkThreads, 2) fft_pkp_pass_kernel(const IlPas
 template <int N, int R0, int R1, int R2, bool SI, bool SO>
 static int launch_pkp_pass(cudaStream_t s, const IlPassArgs &a) {
     static bool attr_done[64] = {false};
-    const size_t smem = pk_buf_floats(N) * sizeof(float) + (size_t)N * kSpecL * sizeof(c64);
+    const size_t smem = pk_buf_floats(N) * sizeof(float) + (size_t)N * kSpecL * sizeof(c64) + (size_t)N * sizeof(c64);
     if ((int64_t)smem > smem_optin()) return -100;
     int dev = 0;
     IB200_TRY(cudaGetDevice(&dev));
@@ -274,15 +278,17 @@ template <int N, int R0, int R1, int R2>
 __global__ void __launch_bounds__(kPkThreads, 2) sense_expand_pk_kernel(const SenseFftArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     sense_expand_pk_body<N, R0, R1, R2, kPkThreads>(a, reinterpret_cast<float *>(smem_raw), (int64_t)blockIdx.x, (int)threadIdx.x,
-                                        (int)blockDim.x);
+                                                    (int)blockDim.x);
 }
 
 template <int N, int R0, int R1, int R2>
 __global__ void __launch_bounds__(kPkThreads, 2) sense_combine_pk_kernel(const SenseFftArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *buf = reinterpret_cast<float *>(smem_raw);
-    sense_combine_pk_body<N, R0, R1, R2, kPkThreads>(a, buf, reinterpret_cast<c64 *>(buf + pk_smem_floats(N, R2 > 1, true)),
-                                         (int64_t)blockIdx.x, (int)threadIdx.x, (int)blockDim.x);
+    c64 *acc = reinterpret_cast<c64 *>(buf + pk_smem_floats(N, R2 > 1, true));
+    // (a shared-memory twiddle table, which pays in the persistent strided passes, costs these one-shot kernels
+    // registers they do not have: measured slower)
+    sense_combine_pk_body<N, R0, R1, R2, kPkThreads>(a, buf, acc, (int64_t)blockIdx.x, (int)threadIdx.x, (int)blockDim.x);
 }
 
 // returns 0 when launched, -100 when the packed kernels do not apply
@@ -444,7 +450,7 @@ static bool sense_z_pass_is_persistent(const ib200_sense_plan_s *p) {
 #define IB200_PKP_OK(n, r0, r1, r2)                                                                         \
     if (fft_spec_matches(k, n, r0, r1, r2))                                                                 \
         ok = pkp_mid_pairs(n, r1, r2, kPkThreads) <= 16 &&                                                  \
-             (int64_t)(pk_buf_floats(n) * sizeof(float) + (size_t)n * kSpecL * sizeof(c64)) <= smem_optin();
+             (int64_t)(pk_buf_floats(n) * sizeof(float) + (size_t)n * kSpecL * sizeof(c64) + (size_t)n * sizeof(c64)) <= smem_optin();
     IB200_FFT_SPEC_LIST(IB200_PKP_OK)
 #undef IB200_PKP_OK
     return ok;

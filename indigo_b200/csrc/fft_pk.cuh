@@ -438,10 +438,11 @@ IB_HD constexpr int pkp_mid_pairs(int n, int r1, int r2, int nt) { return r2 > 1
 // one tile whose input already sits in raw[]; prefetches `next` (< 0: none) once raw[] is free.
 // NT = threads of the CTA (0 in the single-threaded emulation)
 template <int N, int R0, int R1, int R2, bool SWAP_IN, bool SWAP_OUT, int NT>
-IB_HD void fft_pkp_tile_body(const IlPassArgs &a, int64_t tile, int64_t next, float *bufA, c64 *raw, int tid, int nt) {
+IB_HD void fft_pkp_tile_body(const IlPassArgs &a, int64_t tile, int64_t next, float *bufA, c64 *raw, int tid, int nt,
+                             const c64 *tw = nullptr) {
     constexpr bool THREE = R2 > 1;
     PkPrefCtx<SWAP_IN, SWAP_OUT> c;
-    c.raw = raw; c.gout = const_cast<c64 *>(pkp_tile_base(a, tile)); c.tw = a.tw; c.pstride = a.pstride;
+    c.raw = raw; c.gout = const_cast<c64 *>(pkp_tile_base(a, tile)); c.tw = tw ? tw : a.tw; c.pstride = a.pstride;
     int lo, hi;
     pkp_tile_window(a, tile, true, lo, hi);
     c.in0 = lo; c.inlen = (unsigned)(hi - lo);
@@ -489,14 +490,15 @@ struct PkXCtx {
 };
 
 template <int N, int R0, int R1, int R2, int NT>
-IB_HD void sense_expand_pk_body(const SenseFftArgs &a, float *bufA, int64_t block, int tid, int nt) {
+IB_HD void sense_expand_pk_body(const SenseFftArgs &a, float *bufA, int64_t block, int tid, int nt,
+                                const c64 *tw = nullptr) {
     const XTile t = sense_x_tile(a.C);
     const int ygroups = (a.N1 + t.YY - 1) / t.YY;
     const int y = (int)(block % ygroups) * t.YY, z = (int)(block / ygroups);
     const int rows = a.N1 - y < t.YY ? a.N1 - y : t.YY;
     const int64_t vox0 = ((int64_t)z * a.N1 + y) * a.N0;
     PkXCtx c;
-    c.tw = a.tw; c.C = a.C; c.N0 = a.N0; c.off0 = a.off0;
+    c.tw = tw ? tw : a.tw; c.C = a.C; c.N0 = a.N0; c.off0 = a.off0;
     c.lmask = t.YY > 1 ? t.CT - 1 : 0x7fffffff; c.lshift = t.YY > 1 ? t.shift : 31;
     c.rowstride = (int64_t)a.n0 * a.C;
     c.img = a.img + vox0; c.pf = a.pf + vox0 * a.C;
@@ -545,7 +547,8 @@ struct PkXInCtx {
 };
 
 template <int N, int R0, int R1, int R2, int NT>
-IB_HD void sense_combine_pk_body(const SenseFftArgs &a, float *bufA, c64 *acc, int64_t block, int tid, int nt) {
+IB_HD void sense_combine_pk_body(const SenseFftArgs &a, float *bufA, c64 *acc, int64_t block, int tid, int nt,
+                                 const c64 *tw = nullptr) {
     constexpr bool THREE = R2 > 1;
     const XTile t = sense_x_tile(a.C);
     const int ygroups = (a.N1 + t.YY - 1) / t.YY;
@@ -554,7 +557,7 @@ IB_HD void sense_combine_pk_body(const SenseFftArgs &a, float *bufA, c64 *acc, i
     const int64_t vox0 = ((int64_t)z * a.N1 + y) * a.N0;
     float *bufB = bufA + pk_buf_floats(N);
     PkXInCtx c;
-    c.tw = a.tw; c.C = a.C; c.N0 = a.N0; c.off0 = a.off0;
+    c.tw = tw ? tw : a.tw; c.C = a.C; c.N0 = a.N0; c.off0 = a.off0;
     c.lmask = t.YY > 1 ? t.CT - 1 : 0x7fffffff; c.lshift = t.YY > 1 ? t.shift : 31;
     c.rowstride = (int64_t)a.n0 * a.C;
     c.resplane = N * kSpecL;

@@ -8,11 +8,14 @@ on column-major (grid, coil) arrays.  On the B200 the sa
 arithmetic runs as
 
     ib200_sense_expand_fft      grid = FFT3(zpad(pf .* x))           coil-interleaved grid[z][y][x][c],
-                                                                      zero rows never touched (pruned passes)
-    ib200_ccsrmm_il  (G')       k    = G' grid                        one 128-byte line per stored entry
-    ib200_ccsrmm_il  (G'^H)     grid = G'^H k                         stored adjoint, rows in tile-major order
+                                                                      zero rows never touched (pruned passes),
+                                                                      last pass stores only inside the support
+    ib200_kb_gather   (G')      k    = G' grid                        no stored matrix: separable 96-byte records,
+                                                                      one 128-byte line per tap
+    ib200_ccsrmm_runs (G'^H)    grid = G'^H k                         stored adjoint merged into x-runs of 4 points
     ib200_sense_ifft_combine    y    = sum_c conj(pf) .* crop(IFFT3(grid))
 
+(fallbacks on stored entries: ib200_ccsrmm_ilr / ib200_ccsrmm_il; every stage has a switch on SenseDevice)
 so the 9.2 GB zero-padded volume of cfg3 is never written by a scatter, read back by the FFT,
 or transposed between the coil-slow layout of the interface and the coil-fast layout the
 gather wants.  The node below is an ordinary operator of the tree family the backend uses
@@ -105,24 +108,23 @@ class SenseDevice(object):
                 lib.csr_pack_real(s, self.nnz, self.t_val.ptr, self.t_ind.ptr, t_pk.ptr, hmax)
                 self.t_pk, self.real = t_pk, True
                 self.t_val = self.t_ind = None                          # the complex copy of G'^H is not needed any more
-                # samples sorted by the 8x8x8 grid tile they fall into: the rows one CTA owns then share
-                # operand lines in all three dimensions (L1) and neighbouring CTAs share them in L2
+                # samples sorted by the 8x8x8 grid tile they fall into, tiles grouped into 64^3 super-tiles: the
+                # samples one CTA sweeps share operand lines in all three dimensions (L1) and the CTAs in
+                # flight cover a compact block of the grid (L2)
                 stile = (ctypes.c_int64 * 3)(*self.sample_tile)
                 ssuper = (ctypes.c_int64 * 3)(*self.sample_super)
                 lib.grid_tile_rank2(s, grid3, stile, ssuper, None, ctypes.byref(padded))
                 nr8 = int(padded.value)
                 rank8 = B.empty_array((self.on,), i32)
-                junk = None
                 lib.grid_tile_rank2(s, grid3, stile, ssuper, rank8.ptr, ctypes.byref(padded))
                 self.g_ptr = B.empty_array((self.M + 1,), i32, name='G.sorted.rowPtrs')
                 self.g_pk = B.zero_array((self.nnz + 2,), pk, name='G.sorted.packed')
                 self.g_map = B.empty_array((max(self.M, 1),), i32, name='G.sorted.rowmap')
                 lib.csr_permute_rows(s, self.M, self.nnz, self.G.rowPtrs.ptr, g_pk.ptr, rank8.ptr, nr8,
                                      self.g_ptr.ptr, self.g_pk.ptr, self.g_map.ptr)
-                del rank8, junk
+                del rank8
                 # separable Kaiser-Bessel records in the same tile-sorted order: the forward gather then
-                # needs no stored entries at all (csrc/kbgrid.cu)
-                # k-space between the two gridding steps is kept in this sorted order when both the separable
+                # needs no stored entries at all (csrc/kbgrid.cu).  k-space between the two gridding steps is kept in this sorted order when both the separable
                 # forward gather and the x-run adjoint gather serve it: samples that are neighbours on the grid
                 # are then neighbours in memory (the original spoke order scatters them over 0.9 GB at cfg3)
                 self.kb = None

@@ -131,6 +131,57 @@ def test_fused_cg_iterates(B):
     assert worst < TOL, worst
 
 
+def test_reduced_cfg4_32_coils_cg(B):
+    """BASELINE config 4 at reduced size: 32 coils on one GPU (the fused recipe's maximum), sqrt-DCF rows,
+    lamda passed through cg(lamda=) (well-conditioned protocol of DESIGN.md section 5, 0.05 ||A^H A||):
+    A^H A x and all 50 CG iterates within 1e-5 of the oracle."""
+    N, C = (26, 26, 26), 32
+    rs, coord, maps, w = _setup(N, C, "koosh", True, seed=5)
+    A = sense_operator_fused(B, N, coord, maps, 2.0, weights=w)
+    assert A._dev.runs is not None and A._dev.kb is not None
+    AHA = normal_operator(A)
+    ref = osense.SenseOperator(N, coord, maps, 2.0, weights=w)
+    x = synth.rand64c(rs, int(np.prod(N)), 1)
+    want = ref.normal(x)
+    assert relerr(AHA * x, want) < TOL
+    b = (want / np.abs(want).max()).astype(C64)
+    lam = 0.05 * osense.spectral_norm(ref)
+    mine, theirs = [], []
+    B.cg(AHA, b, np.zeros_like(b, order='F'), lamda=lam, maxiter=50, tol=0.0, iterates=mine)
+    K.cg(ref.normal_into, b, np.zeros_like(b), lamda=lam, tol=0.0, maxiter=50, iterates=theirs)
+    worst = max(relerr(m, t) for m, t in zip(mine, theirs))
+    assert worst < TOL, worst
+
+
+def test_reduced_cfg5_spirals_with_coil_compression(B):
+    """BASELINE config 5 at reduced size: stack-of-spirals trajectory, multi-coil k-space compressed by a
+    DenseMatrix (cgemm, coil-fastest data: tall-skinny GEMM) to virtual coils, then the fused NUFFT of the
+    virtual coils.  Every stage against the numpy oracle."""
+    N, Cv, Cfull = (16, 16, 16), 6, 24
+    rs = np.random.RandomState(21)
+    coord = synth.stack_of_spirals(nz=16, nleaves=6, nread=96, turns=4.0)
+    ns = int(np.prod(coord.shape[1:]))
+    # coil compression matrix: first Cv left singular vectors of a calibration block (SURVEY 8d, cfg5)
+    calib = synth.rand64c(rs, Cfull, 64)
+    U = np.linalg.svd(calib.astype(np.complex128), full_matrices=False)[0][:, :Cv]
+    Mc = np.asfortranarray(U.conj().T.astype(C64))                       # Cv x Cfull
+    ksp = synth.rand64c(rs, Cfull, ns)                                   # coil-fastest k-space
+    yd = B.zero_array((Cv, ns), C64)
+    B.cgemm(yd, B.copy_array(Mc), B.copy_array(ksp), 1.0, 0.0, forward=True)
+    comp = yd.to_host()
+    assert relerr(comp, Mc.astype(np.complex128) @ ksp.astype(np.complex128)) < TOL
+    # virtual-coil operator: maps compressed the same way, unit RSS
+    maps = synth.unit_rss_maps(rs, N, Cv)
+    A = sense_operator_fused(B, N, coord, maps, 2.0)
+    ref = osense.SenseOperator(N, coord, maps, 2.0)
+    x = synth.rand64c(rs, int(np.prod(N)), 1)
+    assert relerr(A * x, ref.forward(x)) < TOL
+    # adjoint applied to the compressed data (sample-fastest per coil, as Operator.eval expects)
+    y = np.asfortranarray(comp.T.reshape((-1, 1), order='F'))
+    assert relerr(A.H * y, ref.adjoint(y)) < TOL
+    assert relerr(normal_operator(A) * x, ref.normal(x)) < TOL
+
+
 def test_fused_matches_six_call_tree_at_size(B):
     """64^3 image, 128^3 grid, 8 coils, 20k samples: beyond the oracle's reach in a test, so the fused
     path is compared with the (oracle-checked) six-call tree on the same device-built matrices, and the
