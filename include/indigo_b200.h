@@ -334,6 +334,11 @@ int ib200_cgemm(void *stream, int conjtrans, int64_t m, int64_t n, int64_t k, fl
 int ib200_csymm(void *stream, int left, int64_t m, int64_t n, float alpha_re, float alpha_im,
                 const void *M, int64_t ldm, const void *X, int64_t ldx, float beta_re, float beta_im,
                 void *Y, int64_t ldy);
+/* Products with at most 64 rows of op(M), an even k and 16-byte aligned X columns (coil compression:
+ * M 12 x 48, millions of coil-fastest columns) run on the tensor cores as three TF32 MMAs per
+ * product on (hi, lo) operand splits; everything else on the SIMT fp32 kernel.
+ * mode 1 forces the SIMT kernel (tests compare the two), mode 0 restores the automatic choice. */
+int ib200_cgemm_mode(int mode);
 
 #ifdef __cplusplus
 }

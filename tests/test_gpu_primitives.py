@@ -326,6 +326,89 @@ def test_cgemm(B, m, n, k, alpha, beta, forward):
     assert relerr(yd.to_host(), want) < 1e-5 or np.allclose(yd.to_host(), want, atol=1e-4)
 
 
+@pytest.fixture
+def simt_gemm(B):
+    """Switch handle for the two cgemm kernels: simt_gemm(True) forces the SIMT kernel."""
+    def force(on):
+        B._lib.cgemm_mode(1 if on else 0)
+    yield force
+    B._lib.cgemm_mode(0)
+
+
+# tall-skinny products (coil compression, SURVEY 8 row a6): the tensor-core 3xTF32 kernel.  Shapes walk the
+# n-tile instantiations (m up to 64), k groups with a half-empty tail (k % 8 != 0), ragged column counts.
+TC_SHAPES = [(12, 48, 5000), (48, 12, 5000), (6, 24, 1000), (1, 2, 33), (64, 6, 777), (17, 10, 4099), (33, 22, 100),
+             (4, 96, 257), (24, 14, 64), (3, 192, 48)]
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+@pytest.mark.parametrize("alpha,beta", [(1, 0), (0.5 + 0.5j, 0.5 - 0.25j)])
+@pytest.mark.parametrize("forward", [True, False])
+def test_cgemm_tensor_core(B, simt_gemm, shape, alpha, beta, forward):
+    """Y = alpha*op(M)*X + beta*Y on the tensor cores against the fp64 product: three TF32 MMAs on (hi, lo)
+    splits must stay at complex64 accuracy (plain TF32 would sit near 1e-3), and agree with the SIMT kernel."""
+    m, k, n = shape
+    rs = np.random.RandomState(m * 1000 + k)
+    M = synth.rand64c(rs, m, k) if forward else synth.rand64c(rs, k, m)
+    x, y = synth.rand64c(rs, k, n), synth.rand64c(rs, m, n)
+    opM = M if forward else M.conj().T
+    want = alpha * (opM.astype(np.complex128) @ x.astype(np.complex128)) + beta * y.astype(np.complex128)
+    Md, xd = B.copy_array(M), B.copy_array(x)
+    yd = B.copy_array(y)
+    B.cgemm(yd, Md, xd, alpha, beta, forward=forward)
+    got = yd.to_host()
+    # the tensor cores truncate when they align the addends of the fp32 accumulator: a chain of 3*k/4 MMAs on
+    # all-positive data (rand64c) drifts by ~2^-24 per MMA; 2e-6 up to cfg5's k = 48, the 1e-5 parity bar beyond
+    tol = 2e-6 if k <= 64 else 1e-5
+    assert relerr(got, want) < tol, relerr(got, want)
+    simt_gemm(True)
+    ys = B.copy_array(y)
+    B.cgemm(ys, Md, xd, alpha, beta, forward=forward)
+    assert relerr(ys.to_host(), want) < 2e-6
+    assert relerr(got, ys.to_host()) < tol
+
+
+def test_cgemm_tensor_core_leading_dims(B):
+    """Raw C-ABI call with ldx > k and ldy > m (arena slices): padding rows of Y stay untouched."""
+    m, k, n, ldx, ldy = 12, 48, 1500, 52, 14
+    rs = np.random.RandomState(5)
+    M, xf, yf = synth.rand64c(rs, m, k), synth.rand64c(rs, ldx, n), synth.rand64c(rs, ldy, n)
+    Md, xd, yd = B.copy_array(M), B.copy_array(xf), B.copy_array(yf)
+    B._lib.cgemm(B._stream, 0, m, n, k, 2.0, -1.0, Md.ptr, m, xd.ptr, ldx, 0.0, 0.0, yd.ptr, ldy)
+    got = yd.to_host()
+    want = (2 - 1j) * (M.astype(np.complex128) @ xf[:k].astype(np.complex128))
+    assert relerr(got[:m], want) < 2e-6
+    np.testing.assert_array_equal(got[m:], yf[m:])
+
+
+def test_cgemm_cfg5_shape_at_size(B, simt_gemm):
+    """12 x 48 compression matrix on 2^20 coil-fastest columns (cfg5 has 12.6 M): tensor-core kernel against the
+    SIMT kernel on the device (norm of the difference), against fp64 on a slice, and compression followed by
+    expansion with an orthonormal basis is a projection (idempotent): size-independent check."""
+    m, k, n = 12, 48, 1 << 20
+    rs = np.random.RandomState(48)
+    U = np.linalg.svd(synth.rand64c(rs, k, 64).astype(np.complex128), full_matrices=False)[0][:, :m]
+    M = np.asfortranarray(U.conj().T.astype(C64))
+    x = synth.rand64c(rs, k, n)
+    Md, xd = B.copy_array(M), B.copy_array(x)
+    y1, y2 = B.zero_array((m, n), C64), B.zero_array((m, n), C64)
+    B.cgemm(y1, Md, xd, 1.0, 0.0, forward=True)
+    simt_gemm(True); B.cgemm(y2, Md, xd, 1.0, 0.0, forward=True); simt_gemm(False)
+    ref2 = B.norm2(y2)
+    B.axpby(1.0, y2, -1.0, y1)
+    assert np.sqrt(B.norm2(y2) / ref2) < 2e-6
+    cols = slice(n - 4099, n)
+    got = y1.to_host()[:, cols]
+    assert relerr(got, M.astype(np.complex128) @ x[:, cols].astype(np.complex128)) < 2e-6
+    # P = M^H M is a projector: M (M^H (M x)) = M x
+    back, again = B.zero_array((k, n), C64), B.zero_array((m, n), C64)
+    B.cgemm(back, Md, y1, 1.0, 0.0, forward=False)
+    B.cgemm(again, Md, back, 1.0, 0.0, forward=True)
+    ref1 = B.norm2(y1)
+    B.axpby(1.0, again, -1.0, y1)
+    assert np.sqrt(B.norm2(again) / ref1) < 5e-6
+
+
 @pytest.mark.parametrize("m,k,alpha,beta,left", list(product([2, 5, 6, 40], [1, 3], [0.0, 1.5], [0.0, 0.5], [True, False])))
 def test_csymm(B, m, k, alpha, beta, left):
     rs = np.random.RandomState(m + k)
