@@ -82,10 +82,23 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
 }
+// (hi, lo) TF32 split of an fp32 operand in three instructions: hi = x rounded to 10 mantissa bits by an integer
+// add-and-mask on the bit pattern (round half away from zero, what cvt.rna does in nine instructions with its
+// NaN handling), lo = x - hi exactly; the tensor cores ignore the 13 low mantissa bits of a TF32 operand, so lo
+// needs no rounding of its own (|x - hi - tf32(lo)| <= 2^-22 |x|).
+__device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) {
+    hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float2 ldg_stream2(const float *p) {
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
 }
 __device__ __forceinline__ float4 ldg_stream4(const float *p) {
     float4 v;
@@ -101,26 +114,34 @@ static const int TC_KCHUNK = 6;       // 16-float k groups held in registers at 
 //   M'[2i][2l] = Re W, M'[2i][2l+1] = -Im W, M'[2i+1][2l] = Im W, M'[2i+1][2l+1] = Re W.
 // Lane (g = lane/4, t = lane%4) of k group G holds the floats 16G + 4t .. 4t+3 of columns g and g+8:
 // .x/.y feed k-step 2G (fragment slots t and t+4), .z/.w feed k-step 2G+1, and the fragment table
-// uses the same assignment, so the permutation of the reduction order cancels.
+// uses the same assignment, so the permutation of the reduction order cancels.  A last group of only 8
+// floats (k % 8 == 4) is a single k-step on floats 16G + 2t, 2t+1.
 // One 16-column tile of X as fragment registers: KC k groups for columns j0 = 16*tile + g and j0 + 8.
 template <int KC>
 __device__ __forceinline__ void tc_load_tile(float4 (&a0)[KC], float4 (&a1)[KC], const float *__restrict__ X, int64_t ldx2,
                                              int64_t tile, int64_t n, int G0, int K2, int g, int t) {
     const int64_t j0 = tile * 16 + g, j1 = j0 + 8;
-    const float *x0 = X + j0 * ldx2 + 4 * t, *x1 = X + j1 * ldx2 + 4 * t;
+    const float *x0 = X + j0 * ldx2, *x1 = X + j1 * ldx2;
 #pragma unroll
     for (int u = 0; u < KC; ++u) {
         const int G = G0 + u;
-        const bool ok = 16 * G + 4 * t + 3 < K2;                  // K2 % 4 == 0: a lane's four floats are all in or all out
-        a0[u] = (ok && j0 < n) ? ldg_stream4(x0 + 16 * G) : make_float4(0.f, 0.f, 0.f, 0.f);
-        a1[u] = (ok && j1 < n) ? ldg_stream4(x1 + 16 * G) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (K2 - 16 * G == 8) {                                   // tail of 8 floats: one k-step, two floats per lane
+            const float2 p0 = j0 < n ? ldg_stream2(x0 + 16 * G + 2 * t) : make_float2(0.f, 0.f);
+            const float2 p1 = j1 < n ? ldg_stream2(x1 + 16 * G + 2 * t) : make_float2(0.f, 0.f);
+            a0[u] = make_float4(p0.x, p0.y, 0.f, 0.f);
+            a1[u] = make_float4(p1.x, p1.y, 0.f, 0.f);
+        } else {
+            const bool ok = 16 * G + 4 * t + 3 < K2;              // K2 % 4 == 0: a lane's four floats are all in or all out
+            a0[u] = (ok && j0 < n) ? ldg_stream4(x0 + 16 * G + 4 * t) : make_float4(0.f, 0.f, 0.f, 0.f);
+            a1[u] = (ok && j1 < n) ? ldg_stream4(x1 + 16 * G + 4 * t) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
 }
 
 // acc += X-tile fragments (k groups G0 .. G0+KC-1) times the fragment table: three TF32 MMAs per product.
 template <int NT, int KC>
 __device__ __forceinline__ void tc_mma_tile(float (&acc)[NT][4], const float4 (&a0)[KC], const float4 (&a1)[KC],
-                                            const float4 *bfrag, int G0, int KG, int lane) {
+                                            const float4 *bfrag, int G0, int KG, int K2, int lane) {
 #pragma unroll
     for (int u = 0; u < KC; ++u) {
         const int G = G0 + u;
@@ -128,12 +149,10 @@ __device__ __forceinline__ void tc_mma_tile(float (&acc)[NT][4], const float4 (&
             const float v[2][4] = {{a0[u].x, a1[u].x, a0[u].y, a1[u].y}, {a0[u].z, a1[u].z, a0[u].w, a1[u].w}};
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
+                if (h == 1 && K2 - 16 * G == 8) break;            // tail group: a single k-step
                 uint32_t ah[4], al[4];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    ah[r] = to_tf32(v[h][r]);
-                    al[r] = to_tf32(v[h][r] - __uint_as_float(ah[r]));
-                }
+                for (int r = 0; r < 4; ++r) split_tf32(v[h][r], ah[r], al[r]);
                 const float4 *bp = bfrag + (size_t)((2 * G + h) * NT) * 32 + lane;
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
@@ -183,7 +202,9 @@ cgemm_tc_kernel(int m, int k, int64_t n, c64 alpha, const c64 *__restrict__ Mp, 
     for (int e = threadIdx.x; e < KG * 2 * NT * 32; e += blockDim.x) {
         const int lane = e & 31, nt = (e >> 5) % NT, s = (e >> 5) / NT;
         const int o = nt * 8 + (lane >> 2), i = o >> 1;
-        const int l = (16 * (s >> 1) + 4 * (lane & 3) + 2 * (s & 1)) >> 1;
+        const int G = s >> 1;
+        const int l = (K2 - 16 * G == 8) ? ((s & 1) ? k : (16 * G + 2 * (lane & 3)) >> 1)       // tail of 8 floats: one k-step
+                                         : (16 * G + 4 * (lane & 3) + 2 * (s & 1)) >> 1;
         float b0 = 0.f, b1 = 0.f;
         if (i < m && l < k) {
             c64 w = __ldg(Mp + i * sa_i + l * sa_l);
@@ -208,7 +229,7 @@ cgemm_tc_kernel(int m, int k, int64_t n, c64 alpha, const c64 *__restrict__ Mp, 
             float acc[NT][4];
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-            tc_mma_tile<NT, KC>(acc, c0, c1, bfrag, 0, KG, lane);
+            tc_mma_tile<NT, KC>(acc, c0, c1, bfrag, 0, KG, K2, lane);
             tc_store_tile<NT>(acc, Y, ldy2, tile, n, m, beta, beta_zero, g, t);
 #pragma unroll
             for (int u = 0; u < KC; ++u) { c0[u] = n0[u]; c1[u] = n1[u]; }
@@ -222,13 +243,286 @@ cgemm_tc_kernel(int m, int k, int64_t n, c64 alpha, const c64 *__restrict__ Mp, 
         for (int G0 = 0; G0 < KG; G0 += KC) {
             float4 a0[KC], a1[KC];
             tc_load_tile<KC>(a0, a1, X, ldx2, tile, n, G0, K2, g, t);
-            tc_mma_tile<NT, KC>(acc, a0, a1, bfrag, G0, KG, lane);
+            tc_mma_tile<NT, KC>(acc, a0, a1, bfrag, G0, KG, K2, lane);
         }
         tc_store_tile<NT>(acc, Y, ldy2, tile, n, m, beta, beta_zero, g, t);
     }
 }
 
-static int g_gemm_mode = 0;           // 0 = automatic, 1 = SIMT only (tests compare the two paths)
+// ---------------------------------------------------------------- tcgen05 path
+// The same real-form product on the 5th-generation tensor cores: D(128 columns of X  x  N real outputs) in
+// TMEM, A = 128 columns of X (K-major: the interleaved floats of a column are the reduction index), B =
+// alpha*op(M)' (N x 2k, K-major), both in shared memory in the canonical no-swizzle K-major layout (8-row x
+// 16-byte core matrices; SBO = 128 bytes between row groups, LBO between 16-byte k slices), hi and lo TF32
+// planes of each; per 8-float k-step one elected thread issues lo*hi + hi*lo + hi*hi (kind::tf32, fp32
+// accumulate).  The CUDA cores only move data: global -> registers (one k chunk of <= 48 floats per column,
+// two chunks in flight per CTA) -> split -> shared, and TMEM -> registers -> global for the result.
+namespace t5 {
+
+static const int ROWS = 128, THREADS = 256, RPT = 6, KCH_MAX = 48;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor, no swizzle, version 1 (sm_100): start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void mma_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    for (uint32_t spin = 0; !mbar_try(bar, parity); ++spin)
+        if (spin > (1u << 22)) __trap();                   // a lost arrival becomes a launch error, not a hang
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+struct Ctx {
+    const float *X; int64_t ldx2, n, ntiles;
+    int KCH, CPR;                      // floats / 16-byte slices per column per k chunk
+    uint32_t lbo_a, lbo_b;
+    unsigned char *a_hi, *a_lo, *b_cat;   // b_cat: rows 0..N-1 = hi plane of alpha*op(M)', rows N..2N-1 = lo plane
+    uint64_t *bar;
+    uint32_t tmem, idesc_cat, idesc_hi;   // MMA shapes 128 x 2N and 128 x N
+    uint32_t rc[RPT];                  // this thread's (column-in-tile, slice) per load slot: r | slice << 8
+};
+
+__device__ __forceinline__ void load_chunk(float4 (&rb)[RPT], const Ctx &c, int64_t tile, int ch) {
+#pragma unroll
+    for (int it = 0; it < RPT; ++it) {
+        const int q = it * THREADS + threadIdx.x, r = c.rc[it] & 255, sl = c.rc[it] >> 8;
+        const int64_t col = tile * ROWS + r;
+        rb[it] = (q < ROWS * c.CPR && tile < c.ntiles && col < c.n) ? ldg_stream4(c.X + col * c.ldx2 + ch * c.KCH + sl * 4)
+                                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// one k chunk of one tile: registers -> (hi, lo) operand planes -> MMAs; then the loads two steps ahead
+__device__ __forceinline__ void step(float4 (&rb)[RPT], const Ctx &c, int ch, bool first, int64_t next_tile, int next_ch,
+                                     uint32_t &phase) {
+#pragma unroll
+    for (int it = 0; it < RPT; ++it) {
+        const int q = it * THREADS + threadIdx.x, r = c.rc[it] & 255, sl = c.rc[it] >> 8;
+        if (q < ROWS * c.CPR) {
+            const float4 v = rb[it];
+            uint4 h, l;
+            split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+            const uint32_t off = (uint32_t)sl * c.lbo_a + (uint32_t)r * 16;
+            *reinterpret_cast<uint4 *>(c.a_hi + off) = h;
+            *reinterpret_cast<uint4 *>(c.a_lo + off) = l;
+        }
+    }
+    fence_async_smem();                                    // generic-proxy stores -> visible to the tensor-core (async) proxy
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        fence_after();
+        const uint32_t ah = smem_u32(c.a_hi), al = smem_u32(c.a_lo), bc = smem_u32(c.b_cat);
+        for (int ks = 0; ks < c.KCH / 8; ++ks) {
+            const uint32_t ao = (uint32_t)(2 * ks) * c.lbo_a, bo = (uint32_t)(ch * c.CPR + 2 * ks) * c.lbo_b;
+            const uint64_t dah = make_desc(ah + ao, c.lbo_a, 128), dal = make_desc(al + ao, c.lbo_a, 128);
+            const uint64_t db = make_desc(bc + bo, c.lbo_b, 128);
+            // D[:, 0:N] += hi*hi, D[:, N:2N] += hi*lo in one MMA on the stacked planes; then D[:, 0:N] += lo*hi:
+            // the X operand, whose shared-memory read is what an MMA this narrow costs, is fetched twice, not 3x
+            mma_ss(c.tmem, dah, db, c.idesc_cat, (first && ks == 0) ? 0u : 1u);
+            mma_ss(c.tmem, dal, db, c.idesc_hi, 1u);
+        }
+        commit(c.bar);
+    }
+    load_chunk(rb, c, next_tile, next_ch);                 // in flight through the MMAs, the epilogue and the next step
+    mbar_wait(c.bar, phase);                               // operand planes free again, accumulator complete
+    phase ^= 1u;
+}
+
+// TMEM (lane = column of X, column = real output 2i + p) -> Y[i, column]
+__device__ __forceinline__ void epilogue(const Ctx &c, int64_t tile, int N, int m, c64 beta, int beta_zero,
+                                         float *__restrict__ Y, int64_t ldy2) {
+    fence_after();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, quarter = warp & 3, half = warp >> 2;
+    const int64_t col = tile * ROWS + quarter * 32 + lane;
+    for (int cb = half * (N / 2); cb < (half + 1) * (N / 2) && cb < 2 * m; cb += 16) {          // warp-uniform bounds
+        uint32_t v[16], w[16];
+        const uint32_t taddr = c.tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cb;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                     : "r"(taddr));
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                     : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
+                       "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+                     : "r"(taddr + (uint32_t)N));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));   // hi*lo half
+        if (col < c.n) {
+            float *yp = Y + col * ldy2 + cb;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = cb / 2 + 2 * j;
+                c64 r0 = mk(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]));
+                c64 r1 = mk(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                if (i + 1 < m) {
+                    if (!beta_zero) {
+                        const float4 o = *reinterpret_cast<const float4 *>(yp + 4 * j);
+                        r0 = cfma(beta, mk(o.x, o.y), r0); r1 = cfma(beta, mk(o.z, o.w), r1);
+                    }
+                    __stcs(reinterpret_cast<float4 *>(yp + 4 * j), make_float4(r0.x, r0.y, r1.x, r1.y));
+                } else if (i < m) {
+                    if (!beta_zero) r0 = cfma(beta, *reinterpret_cast<const c64 *>(yp + 4 * j), r0);
+                    __stcs(reinterpret_cast<c64 *>(yp + 4 * j), r0);
+                }
+            }
+        }
+    }
+    fence_before();
+}
+
+// NCH k chunks per tile (1: 2k <= 48 floats, 2: 2k <= 96 floats, 2k % 16 == 0)
+template <int NCH, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+cgemm_t5_kernel(int m, int k, int N, int tmem_cols, int lbo_pad, int64_t n, c64 alpha, const c64 *__restrict__ Mp, int64_t sa_i,
+                int64_t sa_l, int conjA, const float *__restrict__ X, int64_t ldx2, c64 beta, int beta_zero,
+                float *__restrict__ Y, int64_t ldy2) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    Ctx c;
+    const int K2 = 2 * k;
+    c.X = X; c.ldx2 = ldx2; c.n = n; c.ntiles = (n + ROWS - 1) / ROWS;
+    c.KCH = K2 / NCH; c.CPR = c.KCH / 4;
+    c.lbo_a = ROWS * 16 + lbo_pad; c.lbo_b = (uint32_t)(2 * N) * 16;
+    c.a_hi = smem; c.a_lo = c.a_hi + (size_t)c.CPR * c.lbo_a;
+    c.b_cat = c.a_lo + (size_t)c.CPR * c.lbo_a;
+    c.bar = &bar;
+    // instruction descriptor: fp32 accumulate (bit 4), TF32 A and B (bits 7, 10), both K-major, N >> 3 at 17, M >> 4 at 24
+    c.idesc_hi = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
+    c.idesc_cat = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * N) >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
+#pragma unroll
+    for (int it = 0; it < RPT; ++it) {
+        const int q = it * THREADS + threadIdx.x, r = q / c.CPR;
+        c.rc[it] = (uint32_t)(r & 255) | ((uint32_t)(q - r * c.CPR) << 8);
+    }
+    // alpha*op(M)' as stacked (hi, lo) TF32 planes: element (o, kf) at (kf/4)*LBO_B + (o | o + N)*16 + (kf%4)*4
+    for (int e = threadIdx.x; e < N * K2; e += THREADS) {
+        const int kf = e % K2, o = e / K2, i = o >> 1, l = kf >> 1;
+        float v = 0.f;
+        if (i < m) {
+            c64 w = __ldg(Mp + i * sa_i + l * sa_l);
+            if (conjA) w.y = -w.y;
+            w = cmul(alpha, w);
+            v = (o & 1) ? ((kf & 1) ? w.x : w.y) : ((kf & 1) ? -w.y : w.x);
+        }
+        uint32_t vh, vl;
+        split_tf32(v, vh, vl);
+        const uint32_t off = (uint32_t)(kf >> 2) * c.lbo_b + (uint32_t)o * 16 + (uint32_t)(kf & 3) * 4;
+        *reinterpret_cast<uint32_t *>(c.b_cat + off) = vh;
+        *reinterpret_cast<uint32_t *>(c.b_cat + off + (uint32_t)N * 16) = vl;
+    }
+    fence_async_smem();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_slot)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    c.tmem = tmem_slot;
+
+    uint32_t phase = 0;
+    const int64_t stride = gridDim.x;
+    int64_t tile = blockIdx.x;
+    float4 rb0[RPT], rb1[RPT];
+    if (NCH == 2) {
+        load_chunk(rb0, c, tile, 0);
+        load_chunk(rb1, c, tile, 1);
+        for (; tile < c.ntiles; tile += stride) {
+            step(rb0, c, 0, true, tile + stride, 0, phase);
+            step(rb1, c, 1, false, tile + stride, 1, phase);
+            epilogue(c, tile, N, m, beta, beta_zero, Y, ldy2);
+        }
+    } else {
+        load_chunk(rb0, c, tile, 0);
+        load_chunk(rb1, c, tile + stride, 0);
+        for (; tile < c.ntiles; tile += 2 * stride) {
+            step(rb0, c, 0, true, tile + 2 * stride, 0, phase);
+            epilogue(c, tile, N, m, beta, beta_zero, Y, ldy2);
+            if (tile + stride < c.ntiles) {                // block-uniform
+                step(rb1, c, 0, true, tile + 3 * stride, 0, phase);
+                epilogue(c, tile + stride, N, m, beta, beta_zero, Y, ldy2);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(c.tmem), "r"(tmem_cols) : "memory");
+}
+
+}  // namespace t5
+
+static int g_t5_pad = -1;             // IB200_T5_PAD: bytes added to the k-slice stride of the X operand planes (bank spread)
+
+static size_t t5_smem(int64_t m, int64_t k, int pad) {
+    const int64_t K2 = 2 * k, nch = K2 <= t5::KCH_MAX ? 1 : 2, cpr = K2 / nch / 4, N = (2 * m + 31) / 32 * 32;
+    return (size_t)(2 * cpr * (t5::ROWS * 16 + pad) + 2 * (K2 / 4) * N * 16);
+}
+
+// tcgen05 path: op(M) with <= 64 rows, k a multiple of 4 (8 when two chunks are needed) up to 48, X and Y columns 16-byte aligned
+static bool t5_applicable(int64_t m, int64_t n, int64_t k, const c64 *B, int64_t sb_l, int64_t sb_j, const c64 *C, int64_t ldc) {
+    if (sb_l != 1 || m < 1 || m > 64 || k < 4 || k > 48 || (k & 3) || n < 128) return false;
+    if (2 * k > t5::KCH_MAX && (k & 7)) return false;
+    if ((reinterpret_cast<uintptr_t>(B) & 15) || (sb_j & 1) || (reinterpret_cast<uintptr_t>(C) & 15) || (ldc & 1)) return false;
+    return t5_smem(m, k, 128) <= 100 * 1024;
+}
+
+static int launch_t5(cudaStream_t s, int64_t m, int64_t n, int64_t k, c64 alpha, const c64 *A, int64_t sa_i, int64_t sa_l,
+                     int conjA, const c64 *B, int64_t ldb, c64 beta, c64 *C, int64_t ldc) {
+    if (g_t5_pad < 0) {
+        const char *e = getenv("IB200_T5_PAD");
+        g_t5_pad = e ? atoi(e) : 16;
+        IB200_REQUIRE(g_t5_pad >= 0 && g_t5_pad <= 128 && g_t5_pad % 16 == 0, "IB200_T5_PAD is a multiple of 16 up to 128");
+    }
+    const int N = (int)((2 * m + 31) / 32 * 32);
+    const int tmem_cols = N <= 32 ? 64 : N <= 64 ? 128 : 256;          // accumulator 128 x 2N (hi*hi + lo*hi | hi*lo)
+    const size_t smem = t5_smem(m, k, g_t5_pad);
+    const int nch = 2 * k <= t5::KCH_MAX ? 1 : 2;
+    static int minb = -1;
+    if (minb < 0) { const char *e = getenv("IB200_T5_MINB"); minb = (e && atoi(e) == 3) ? 3 : 2; }
+    auto kern = nch == 1 ? (minb == 3 ? t5::cgemm_t5_kernel<1, 3> : t5::cgemm_t5_kernel<1, 2>)
+                         : (minb == 3 ? t5::cgemm_t5_kernel<2, 3> : t5::cgemm_t5_kernel<2, 2>);
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[nch - 1]) {
+        IB200_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(100 * 1024)));
+        attr_set[nch - 1] = true;
+    }
+    int64_t per_sm = (int64_t)(228 * 1024) / (int64_t)(smem + 1280);
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = ceil_div(n, t5::ROWS);
+    if (grid > per_sm * sm_count()) grid = per_sm * sm_count();
+    kern<<<(unsigned)grid, t5::THREADS, smem, s>>>((int)m, (int)k, N, tmem_cols, g_t5_pad, n, alpha, A, sa_i, sa_l, conjA,
+                                                   (const float *)B, 2 * ldb, beta, (beta.x == 0.f && beta.y == 0.f) ? 1 : 0,
+                                                   (float *)C, 2 * ldc);
+    IB200_LAUNCH_CHECK();
+    return 0;
+}
+
+static int g_gemm_mode = 0;           // 0 = automatic (mma.sync kernel where it applies, else SIMT), 1 = SIMT only,
+                                      // 3 = tcgen05 kernel where it applies (slower today, see the header): tests compare the paths
 
 static int g_gemm_pipe = -1;          // -1 = automatic (short k only), 0 / 1 forced (IB200_CGEMM_PIPE, tools/)
 
@@ -276,6 +570,8 @@ static bool tc_applicable(int64_t m, int64_t n, int64_t k, const c64 *B, int64_t
 static int run_gemm(cudaStream_t s, int64_t m, int64_t n, int64_t k, c64 alpha, const c64 *A, int64_t sa_i,
                     int64_t sa_l, int conjA, const c64 *B, int64_t sb_l, int64_t sb_j, c64 beta, c64 *C, int64_t ldc) {
     if (m == 0 || n == 0) return 0;
+    if (g_gemm_mode == 3 && t5_applicable(m, n, k, B, sb_l, sb_j, C, ldc))
+        return launch_t5(s, m, n, k, alpha, A, sa_i, sa_l, conjA, B, sb_j, beta, C, ldc);
     if (tc_applicable(m, n, k, B, sb_l, sb_j)) {
         const int64_t NT = ceil_div(m, 4);
 #define IB200_TC(N_) return launch_tc<N_>(s, m, n, k, alpha, A, sa_i, sa_l, conjA, B, sb_j, beta, C, ldc)
@@ -304,7 +600,7 @@ using namespace ib200;
 extern "C" {
 
 int ib200_cgemm_mode(int mode) {
-    IB200_REQUIRE(mode == 0 || mode == 1, "mode is 0 (automatic) or 1 (SIMT only)");
+    IB200_REQUIRE(mode == 0 || mode == 1 || mode == 3, "mode is 0 (automatic), 1 (SIMT only) or 3 (tcgen05 where it applies)");
     g_gemm_mode = mode;
     return 0;
 }

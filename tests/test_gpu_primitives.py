@@ -330,7 +330,7 @@ def test_cgemm(B, m, n, k, alpha, beta, forward):
 def simt_gemm(B):
     """Switch handle for the two cgemm kernels: simt_gemm(True) forces the SIMT kernel."""
     def force(on):
-        B._lib.cgemm_mode(1 if on else 0)
+        B._lib.cgemm_mode({False: 0, True: 1, "tcgen05": 3}[on])
     yield force
     B._lib.cgemm_mode(0)
 
@@ -338,13 +338,16 @@ def simt_gemm(B):
 # tall-skinny products (coil compression): the tensor-core 3xTF32 kernel.  Shapes walk the
 # n-tile instantiations (m up to 64), k groups with a half-empty tail (k % 8 != 0), ragged column counts.
 TC_SHAPES = [(12, 48, 5000), (48, 12, 5000), (6, 24, 1000), (1, 2, 33), (64, 6, 777), (17, 10, 4099), (33, 22, 100),
-             (4, 96, 257), (24, 14, 64), (3, 192, 48)]
+             (4, 96, 257), (24, 14, 64), (3, 192, 48),
+             # tcgen05 kernel: one k chunk (2k <= 48) / two chunks, every accumulator width (N = 32 ... 128)
+             (12, 32, 300), (5, 8, 129), (64, 48, 1000), (33, 4, 128), (20, 40, 2500), (48, 24, 1 << 15)]
 
 
 @pytest.mark.parametrize("shape", TC_SHAPES)
 @pytest.mark.parametrize("alpha,beta", [(1, 0), (0.5 + 0.5j, 0.5 - 0.25j)])
 @pytest.mark.parametrize("forward", [True, False])
-def test_cgemm_tensor_core(B, simt_gemm, shape, alpha, beta, forward):
+@pytest.mark.parametrize("path", ["auto", "tcgen05"])
+def test_cgemm_tensor_core(B, simt_gemm, shape, alpha, beta, forward, path):
     """Y = alpha*op(M)*X + beta*Y on the tensor cores against the fp64 product: three TF32 MMAs on (hi, lo)
     splits must stay at complex64 accuracy (plain TF32 would sit near 1e-3), and agree with the SIMT kernel."""
     m, k, n = shape
@@ -355,6 +358,7 @@ def test_cgemm_tensor_core(B, simt_gemm, shape, alpha, beta, forward):
     want = alpha * (opM.astype(np.complex128) @ x.astype(np.complex128)) + beta * y.astype(np.complex128)
     Md, xd = B.copy_array(M), B.copy_array(x)
     yd = B.copy_array(y)
+    simt_gemm("tcgen05" if path == "tcgen05" else False)       # auto: mma.sync kernel; tcgen05: that kernel where it applies
     B.cgemm(yd, Md, xd, alpha, beta, forward=forward)
     got = yd.to_host()
     # the tensor cores truncate when they align the addends of the fp32 accumulator: a chain of 3*k/4 MMAs on

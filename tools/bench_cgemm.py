@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """BASELINE.json configs[4] (cfg5), the coil-compression step: DenseMatrix cgemm of a 12 x 48 matrix on the
 coil-fastest k-space of 128 kz-planes x 48 spirals x 2048 samples (n = 12 582 912 columns), forward
-(compression) and adjoint (expansion), through Backend.cgemm.  Tensor-core 3xTF32 kernel against the SIMT
+(compression) and adjoint (expansion), through Backend.cgemm.  tcgen05 3xTF32 kernel against the mma.sync 3xTF32 kernel, the SIMT
 kernel and the HBM roofline (algorithmic bytes 8*(m*k + k*n + m*n)).  GPU only.
 
     python tools/bench_cgemm.py [--n 12582912] [--reps 10] > profiles/rNN_cgemm_cfg5.md
@@ -23,6 +23,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=128 * 48 * 2048)
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--modes", default="0,3,1", help="cgemm_mode values to time: 0 mma.sync (default path), 3 tcgen05, 1 SIMT")
     args = ap.parse_args()
     peak, src = bench.peaks()
     B = B200Backend(0)
@@ -66,7 +67,9 @@ def main():
     print("|---|---|---:|---:|---:|---:|")
     for label, fn in (("Y(12 x n) = M X  (compression)", lambda: B.cgemm(yd, Md, xd, 1.0, 0.0, forward=True)),
                       ("Z(48 x n) = M^H Y (expansion)", lambda: B.cgemm(zd, Md, yd, 1.0, 0.0, forward=False))):
-        for mode, name in ((0, "tensor core, 3xTF32 (cgemm_tc_kernel)"), (1, "SIMT fp32 (cgemm_kernel)")):
+        for mode, name in ((0, "mma.sync, 3xTF32 (cgemm_tc_kernel; default)"), (3, "tcgen05 + TMEM, 3xTF32 (cgemm_t5_kernel)"), (1, "SIMT fp32 (cgemm_kernel)")):
+            if str(mode) not in args.modes.split(","):
+                continue
             B._lib.cgemm_mode(mode)
             t = timed(fn)
             print("| %s | %s | %.3f | %.0f | %.2f | %.1f |" % (label, name, t, alg / t / 1e6, alg / t / 1e6 / peak, flops / t / 1e9))
