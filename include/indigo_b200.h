@@ -336,8 +336,9 @@ int ib200_csymm(void *stream, int left, int64_t m, int64_t n, float alpha_re, fl
                 void *Y, int64_t ldy);
 /* Products with at most 64 rows of op(M), an even k and 16-byte aligned X columns (coil compression:
  * M 12 x 48, millions of coil-fastest columns) run on the tensor cores as three TF32 MMAs per
- * product on (hi, lo) operand splits; everything else on the SIMT fp32 kernel.
- * mode 1 forces the SIMT kernel (tests compare the two), mode 0 restores the automatic choice. */
+ * product on (hi, lo) operand splits (mma.sync kernel); everything else on the SIMT fp32 kernel.
+ * mode 1 forces the SIMT kernel, mode 3 selects the tcgen05/TMEM kernel where it applies (k % 4 == 0,
+ * k <= 48, n >= 128, 16-byte aligned Y columns; tests compare all three), mode 0 restores the default. */
 int ib200_cgemm_mode(int mode);
 
 #ifdef __cplusplus

@@ -3,18 +3,24 @@
 // (backend.py:487-491); numpy semantics np.py:76-90; the reference GPU path is
 // cublasCgemm/cublasCsymm (cuda.py:314-366).
 //
-// Two kernels:
-//  * cgemm_tc_kernel: the tensor-core path for the shape the SENSE path has
-//    (SURVEY 8 row a6, cfg5 coil compression: op(M) is 12 x 48 or 48 x 12, X has
-//    millions of coil-fastest columns).  The complex product is the real product
-//    Y'(2m x n) = M'(2m x 2k) X'(2k x n) on the interleaved (re, im) floats; the
-//    columns of X are the rows of the m16n8k8 A operand and go from global memory
-//    straight into the fragment registers (one 16-byte load per lane serves two
-//    k-steps, the k order inside the sum being free); alpha*op(M)' is expanded
-//    once per CTA into a per-lane fragment table in shared memory.  Every product
-//    is three TF32 MMAs on the (hi, lo) splits of both operands (lo*hi + hi*lo +
-//    hi*hi, fp32 accumulate): complex64-level accuracy (1e-5 parity bar; plain
-//    TF32 gives 1e-3).  HBM-bound by construction: 8(k+m) bytes per column.
+// Three kernels:
+//  * cgemm_tc_kernel (default for tall-skinny products): the tensor-core path for the shape the SENSE path
+//    has (SURVEY 8 row a6, cfg5 coil compression: op(M) is 12 x 48 or 48 x 12, X has millions of
+//    coil-fastest columns).  The complex product is the real product Y'(2m x n) = M'(2m x 2k) X'(2k x n) on
+//    the interleaved (re, im) floats; the columns of X are the rows of the m16n8k8 A operand and go from
+//    global memory straight into the fragment registers (one 16-byte load per lane serves two k-steps, the
+//    k order inside the sum being free); alpha*op(M)' is expanded once per CTA into a per-lane fragment
+//    table in shared memory.  Every product is three TF32 MMAs on the (hi, lo) splits of both operands
+//    (lo*hi + hi*lo + hi*hi, fp32 accumulate): complex64-level accuracy (6e-7 measured; 1e-5 parity bar;
+//    plain TF32 gives 1e-3).  8(k+m) bytes per column; measured 81 % (12 x 48) / 65 % (48 x 12) of the HBM
+//    copy peak on 12.6 M columns (profiles/r01_s9_cgemm_cfg5.md).
+//  * cgemm_t5_kernel (cgemm_mode 3): the same product on tcgen05.mma with the accumulator in TMEM, operands
+//    in the canonical no-swizzle K-major shared-memory layout, two MMAs per k-step on stacked (hi | lo)
+//    planes of op(M)'.  Parity-green, but 1.6x slower than the mma.sync kernel today: with 24 - 96 real
+//    outputs an MMA costs the shared-memory read of its 128 x 8 X operand (64 cycles measured per 128x32x8
+//    MMA), and the per-tile split -> fence -> MMA -> wait -> epilogue sequence of this first version leaves
+//    a third of the warp samples waiting on the MMA barrier.  Next step: warp-specialised producer /
+//    converter / epilogue roles on a shared-memory ring, X as the 256-wide B operand.
 //  * cgemm_kernel: SIMT fp32 tiles, any shape / leading dimension / alignment;
 //    serves op(M) in {M, M^H} on the left and the real-symmetric right-multiply
 //    through generic element strides.
@@ -166,11 +172,38 @@ __device__ __forceinline__ void tc_mma_tile(float (&acc)[NT][4], const float4 (&
     }
 }
 
-// accumulator (row g | g+8, columns 2t, 2t+1 of n-tile nt) = (re, im) of Y[nt*4 + t, j0 | j1]
+// accumulator (row g | g+8, columns 2t, 2t+1 of n-tile nt) = (re, im) of Y[nt*4 + t, j0 | j1]; with `pair`
+// (even NT, 16-byte aligned Y columns) the fragment table assigns the outputs so that n-tiles 2p and 2p+1
+// hold Y[8p + 2t] and Y[8p + 2t + 1]: one 16-byte store per lane, 64 contiguous bytes per column and instruction
 template <int NT>
 __device__ __forceinline__ void tc_store_tile(const float (&acc)[NT][4], float *__restrict__ Y, int64_t ldy2, int64_t tile,
-                                              int64_t n, int m, c64 beta, int beta_zero, int g, int t) {
+                                              int64_t n, int m, c64 beta, int beta_zero, int pair, int g, int t) {
     const int64_t j0 = tile * 16 + g, j1 = j0 + 8;
+    if (pair) {
+#pragma unroll
+        for (int nt = 0; nt + 1 < NT; nt += 2) {
+            const int i = 4 * nt + 2 * t;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int64_t j = h ? j1 : j0;
+                if (j < n && i < m) {
+                    float *yp = Y + j * ldy2 + 2 * i;
+                    c64 r0 = mk(acc[nt][2 * h], acc[nt][2 * h + 1]), r1 = mk(acc[nt + 1][2 * h], acc[nt + 1][2 * h + 1]);
+                    if (i + 1 < m) {
+                        if (!beta_zero) {
+                            const float4 o = *reinterpret_cast<const float4 *>(yp);
+                            r0 = cfma(beta, mk(o.x, o.y), r0); r1 = cfma(beta, mk(o.z, o.w), r1);
+                        }
+                        __stcs(reinterpret_cast<float4 *>(yp), make_float4(r0.x, r0.y, r1.x, r1.y));
+                    } else {
+                        if (!beta_zero) r0 = cfma(beta, *reinterpret_cast<const c64 *>(yp), r0);
+                        __stcs(reinterpret_cast<c64 *>(yp), r0);
+                    }
+                }
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
         const int i = nt * 4 + t;
@@ -196,12 +229,13 @@ __device__ __forceinline__ void tc_store_tile(const float (&acc)[NT][4], float *
 template <int NT, int KC, bool PIPE>
 __global__ void __launch_bounds__(TC_WARPS * 32)
 cgemm_tc_kernel(int m, int k, int64_t n, c64 alpha, const c64 *__restrict__ Mp, int64_t sa_i, int64_t sa_l, int conjA,
-                const float *__restrict__ X, int64_t ldx2, c64 beta, int beta_zero, float *__restrict__ Y, int64_t ldy2) {
+                const float *__restrict__ X, int64_t ldx2, c64 beta, int beta_zero, float *__restrict__ Y, int64_t ldy2, int pair) {
     extern __shared__ float4 bfrag[];                     // [k-step][n-tile][lane] = (b0 hi, b1 hi, b0 lo, b1 lo)
     const int K2 = 2 * k, KG = (K2 + 15) / 16;
     for (int e = threadIdx.x; e < KG * 2 * NT * 32; e += blockDim.x) {
         const int lane = e & 31, nt = (e >> 5) % NT, s = (e >> 5) / NT;
-        const int o = nt * 8 + (lane >> 2), i = o >> 1;
+        const int n8 = lane >> 2;
+        const int o = pair ? 2 * (8 * (nt >> 1) + 2 * (n8 >> 1) + (nt & 1)) + (n8 & 1) : nt * 8 + n8, i = o >> 1;
         const int G = s >> 1;
         const int l = (K2 - 16 * G == 8) ? ((s & 1) ? k : (16 * G + 2 * (lane & 3)) >> 1)       // tail of 8 floats: one k-step
                                          : (16 * G + 4 * (lane & 3) + 2 * (s & 1)) >> 1;
@@ -230,7 +264,7 @@ cgemm_tc_kernel(int m, int k, int64_t n, c64 alpha, const c64 *__restrict__ Mp, 
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
             tc_mma_tile<NT, KC>(acc, c0, c1, bfrag, 0, KG, K2, lane);
-            tc_store_tile<NT>(acc, Y, ldy2, tile, n, m, beta, beta_zero, g, t);
+            tc_store_tile<NT>(acc, Y, ldy2, tile, n, m, beta, beta_zero, pair, g, t);
 #pragma unroll
             for (int u = 0; u < KC; ++u) { c0[u] = n0[u]; c1[u] = n1[u]; }
         }
@@ -245,7 +279,7 @@ cgemm_tc_kernel(int m, int k, int64_t n, c64 alpha, const c64 *__restrict__ Mp, 
             tc_load_tile<KC>(a0, a1, X, ldx2, tile, n, G0, K2, g, t);
             tc_mma_tile<NT, KC>(acc, a0, a1, bfrag, G0, KG, K2, lane);
         }
-        tc_store_tile<NT>(acc, Y, ldy2, tile, n, m, beta, beta_zero, g, t);
+        tc_store_tile<NT>(acc, Y, ldy2, tile, n, m, beta, beta_zero, pair, g, t);
     }
 }
 
@@ -537,7 +571,8 @@ static int launch_tc2(cudaStream_t s, int64_t m, int64_t n, int64_t k, c64 alpha
     if (grid > cap) grid = cap;
     cgemm_tc_kernel<NT, KC, PIPE><<<(unsigned)grid, TC_WARPS * 32, smem, s>>>(
         (int)m, (int)k, n, alpha, A, sa_i, sa_l, conjA, (const float *)B, 2 * ldb, beta,
-        (beta.x == 0.f && beta.y == 0.f) ? 1 : 0, (float *)C, 2 * ldc);
+        (beta.x == 0.f && beta.y == 0.f) ? 1 : 0, (float *)C, 2 * ldc,
+        (NT % 2 == 0 && !(reinterpret_cast<uintptr_t>(C) & 15) && !(ldc & 1) && !getenv("IB200_CGEMM_NOPAIR")) ? 1 : 0);
     IB200_LAUNCH_CHECK();
     return 0;
 }
