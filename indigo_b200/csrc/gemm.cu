@@ -14,13 +14,16 @@
 //    (lo*hi + hi*lo + hi*hi, fp32 accumulate): complex64-level accuracy (6e-7 measured; 1e-5 parity bar;
 //    plain TF32 gives 1e-3).  8(k+m) bytes per column; measured 81 % (12 x 48) / 65 % (48 x 12) of the HBM
 //    copy peak on 12.6 M columns (profiles/r01_s9_cgemm_cfg5.md).
-//  * cgemm_t5_kernel (cgemm_mode 3): the same product on tcgen05.mma with the accumulator in TMEM, operands
-//    in the canonical no-swizzle K-major shared-memory layout, two MMAs per k-step on stacked (hi | lo)
-//    planes of op(M)'.  Parity-green, but 1.6x slower than the mma.sync kernel today: with 24 - 96 real
-//    outputs an MMA costs the shared-memory read of its 128 x 8 X operand (64 cycles measured per 128x32x8
-//    MMA), and the per-tile split -> fence -> MMA -> wait -> epilogue sequence of this first version leaves
-//    a third of the warp samples waiting on the MMA barrier.  Next step: warp-specialised producer /
-//    converter / epilogue roles on a shared-memory ring, X as the 256-wide B operand.
+//  * cgemm_t5ws_kernel (cgemm_mode 3): the same product on tcgen05.mma with the accumulator in TMEM: one
+//    persistent warp-specialised CTA per SM -- two groups of 8 converter warps (global -> registers -> TF32
+//    split -> operand ring in the canonical no-swizzle K-major shared-memory layout), one MMA warp (two
+//    MMAs per k-step on stacked (hi | lo) planes of op(M)', tcgen05.commit -> mbarriers), four epilogue warps
+//    (tcgen05.ld -> global), two operand stages and two accumulator stages.  Parity-green; 1.29 ms on the
+//    12 x 48 product (71 % of the copy peak) against 1.13 ms for the mma.sync kernel, 2.3 ms on 48 x 12 (its
+//    four epilogue warps write 16-byte pieces of 384-byte columns): an MMA with 24 - 96 real outputs is far
+//    too narrow to amortise the operand staging through shared memory that tcgen05 requires, while mma.sync
+//    takes X straight from global memory into fragments.  Kept selectable for the wider products
+//    (more virtual coils) where the balance turns.
 //  * cgemm_kernel: SIMT fp32 tiles, any shape / leading dimension / alignment;
 //    serves op(M) in {M, M^H} on the left and the real-symmetric right-multiply
 //    through generic element strides.
@@ -104,6 +107,13 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 __device__ __forceinline__ float2 ldg_stream2(const float *p) {
     float2 v;
     asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+// same with a 256-byte L2 prefetch hint: a k chunk reads half of each 384-byte column, the hint brings the
+// other half into L2 while the DRAM page is open
+__device__ __forceinline__ float4 ldg_stream4_pf(const float *p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
 __device__ __forceinline__ float4 ldg_stream4(const float *p) {
@@ -293,7 +303,7 @@ cgemm_tc_kernel(int m, int k, int64_t n, c64 alpha, const c64 *__restrict__ Mp, 
 // two chunks in flight per CTA) -> split -> shared, and TMEM -> registers -> global for the result.
 namespace t5 {
 
-static const int ROWS = 128, THREADS = 256, RPT = 6, KCH_MAX = 48;
+static const int ROWS = 128, THREADS = 256, RPT = 6, KCH_MAX = 48;   // THREADS: converter threads per group, RPT 16-byte pieces each per chunk
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -328,127 +338,93 @@ struct Ctx {
     int KCH, CPR;                      // floats / 16-byte slices per column per k chunk
     uint32_t lbo_a, lbo_b;
     unsigned char *a_hi, *a_lo, *b_cat;   // b_cat: rows 0..N-1 = hi plane of alpha*op(M)', rows N..2N-1 = lo plane
-    uint64_t *bar;
     uint32_t tmem, idesc_cat, idesc_hi;   // MMA shapes 128 x 2N and 128 x N
-    uint32_t rc[RPT];                  // this thread's (column-in-tile, slice) per load slot: r | slice << 8
+    int64_t goff[RPT];                 // this thread's pieces: float offset r*ldx + 4*slice inside a tile chunk,
+    uint32_t soff[RPT];                // byte offset slice*LBO + r*16 inside an operand plane (0xFFFFFFFF: no piece),
+    int rrow[RPT];                     // and the column-in-tile r (for the ragged last tile)
 };
 
 __device__ __forceinline__ void load_chunk(float4 (&rb)[RPT], const Ctx &c, int64_t tile, int ch) {
+    const float *base = c.X + tile * ROWS * c.ldx2 + ch * c.KCH;
+    const int64_t left = c.n - tile * ROWS;                       // columns of X from this tile on (<= 0: past the end)
+    if (tile < c.ntiles && left >= ROWS) {                        // full tile: no per-piece bounds
 #pragma unroll
-    for (int it = 0; it < RPT; ++it) {
-        const int q = it * THREADS + threadIdx.x, r = c.rc[it] & 255, sl = c.rc[it] >> 8;
-        const int64_t col = tile * ROWS + r;
-        rb[it] = (q < ROWS * c.CPR && tile < c.ntiles && col < c.n) ? ldg_stream4(c.X + col * c.ldx2 + ch * c.KCH + sl * 4)
-                                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int it = 0; it < RPT; ++it)
+            rb[it] = c.soff[it] != 0xFFFFFFFFu ? ldg_stream4_pf(base + c.goff[it]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+#pragma unroll
+        for (int it = 0; it < RPT; ++it)
+            rb[it] = (c.soff[it] != 0xFFFFFFFFu && tile < c.ntiles && c.rrow[it] < left) ? ldg_stream4_pf(base + c.goff[it])
+                                                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
-// one k chunk of one tile: registers -> (hi, lo) operand planes -> MMAs; then the loads two steps ahead
-__device__ __forceinline__ void step(float4 (&rb)[RPT], const Ctx &c, int ch, bool first, int64_t next_tile, int next_ch,
-                                     uint32_t &phase) {
+// ---- warp-specialised version: converter warps (global -> registers -> split -> operand ring), one MMA warp,
+// epilogue warps (TMEM -> global); two operand stages and two accumulator stages decouple the three roles, so that
+// loads, MMAs and result stores of different tiles overlap inside one persistent CTA per SM.
+static const int WS_GROUPS = 2, WS_CONV = WS_GROUPS * THREADS, WS_EPI = 128, WS_THREADS = WS_CONV + WS_EPI + 32;
+
+// position in the ring of operand stages: stage index and phase parity, advanced without divisions
+struct Ring {
+    int s, ns; uint32_t ph;
+    __device__ __forceinline__ void advance(int d) { s += d; if (s >= ns) { s -= ns; ph ^= 1u; } }
+};
+
+static const int WS_MAX_STAGES = 4;
+struct WsBars { uint64_t full[WS_MAX_STAGES], empty[WS_MAX_STAGES], tfull[2], tempty[2]; };
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+// converter: one k chunk from registers into operand stage (q & 1)
+__device__ __forceinline__ void ws_convert(const float4 (&rb)[RPT], const Ctx &c, WsBars &bars, uint32_t stage_bytes, const Ring &ring) {
+    const int s = ring.s;
+    mbar_wait(&bars.empty[s], ring.ph ^ 1u);                           // the MMAs that read this stage ns steps ago are done
+    unsigned char *hi = c.a_hi + (size_t)s * stage_bytes, *lo = c.a_lo + (size_t)s * stage_bytes;
 #pragma unroll
     for (int it = 0; it < RPT; ++it) {
-        const int q = it * THREADS + threadIdx.x, r = c.rc[it] & 255, sl = c.rc[it] >> 8;
-        if (q < ROWS * c.CPR) {
+        if (c.soff[it] != 0xFFFFFFFFu) {
             const float4 v = rb[it];
             uint4 h, l;
             split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-            const uint32_t off = (uint32_t)sl * c.lbo_a + (uint32_t)r * 16;
-            *reinterpret_cast<uint4 *>(c.a_hi + off) = h;
-            *reinterpret_cast<uint4 *>(c.a_lo + off) = l;
+            *reinterpret_cast<uint4 *>(hi + c.soff[it]) = h;
+            *reinterpret_cast<uint4 *>(lo + c.soff[it]) = l;
         }
     }
-    fence_async_smem();                                    // generic-proxy stores -> visible to the tensor-core (async) proxy
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        fence_after();
-        const uint32_t ah = smem_u32(c.a_hi), al = smem_u32(c.a_lo), bc = smem_u32(c.b_cat);
-        for (int ks = 0; ks < c.KCH / 8; ++ks) {
-            const uint32_t ao = (uint32_t)(2 * ks) * c.lbo_a, bo = (uint32_t)(ch * c.CPR + 2 * ks) * c.lbo_b;
-            const uint64_t dah = make_desc(ah + ao, c.lbo_a, 128), dal = make_desc(al + ao, c.lbo_a, 128);
-            const uint64_t db = make_desc(bc + bo, c.lbo_b, 128);
-            // D[:, 0:N] += hi*hi, D[:, N:2N] += hi*lo in one MMA on the stacked planes; then D[:, 0:N] += lo*hi:
-            // the X operand, whose shared-memory read is what an MMA this narrow costs, is fetched twice, not 3x
-            mma_ss(c.tmem, dah, db, c.idesc_cat, (first && ks == 0) ? 0u : 1u);
-            mma_ss(c.tmem, dal, db, c.idesc_hi, 1u);
-        }
-        commit(c.bar);
-    }
-    load_chunk(rb, c, next_tile, next_ch);                 // in flight through the MMAs, the epilogue and the next step
-    mbar_wait(c.bar, phase);                               // operand planes free again, accumulator complete
-    phase ^= 1u;
+    fence_async_smem();
+    mbar_arrive(&bars.full[s]);
 }
 
-// TMEM (lane = column of X, column = real output 2i + p) -> Y[i, column]
-__device__ __forceinline__ void epilogue(const Ctx &c, int64_t tile, int N, int m, c64 beta, int beta_zero,
-                                         float *__restrict__ Y, int64_t ldy2) {
-    fence_after();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, quarter = warp & 3, half = warp >> 2;
-    const int64_t col = tile * ROWS + quarter * 32 + lane;
-    for (int cb = half * (N / 2); cb < (half + 1) * (N / 2) && cb < 2 * m; cb += 16) {          // warp-uniform bounds
-        uint32_t v[16], w[16];
-        const uint32_t taddr = c.tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cb;
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                     : "r"(taddr));
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                     : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
-                       "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
-                     : "r"(taddr + (uint32_t)N));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));   // hi*lo half
-        if (col < c.n) {
-            float *yp = Y + col * ldy2 + cb;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int i = cb / 2 + 2 * j;
-                c64 r0 = mk(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]));
-                c64 r1 = mk(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-                if (i + 1 < m) {
-                    if (!beta_zero) {
-                        const float4 o = *reinterpret_cast<const float4 *>(yp + 4 * j);
-                        r0 = cfma(beta, mk(o.x, o.y), r0); r1 = cfma(beta, mk(o.z, o.w), r1);
-                    }
-                    __stcs(reinterpret_cast<float4 *>(yp + 4 * j), make_float4(r0.x, r0.y, r1.x, r1.y));
-                } else if (i < m) {
-                    if (!beta_zero) r0 = cfma(beta, *reinterpret_cast<const c64 *>(yp + 4 * j), r0);
-                    __stcs(reinterpret_cast<c64 *>(yp + 4 * j), r0);
-                }
-            }
-        }
-    }
-    fence_before();
-}
-
-// NCH k chunks per tile (1: 2k <= 48 floats, 2: 2k <= 96 floats, 2k % 16 == 0)
-template <int NCH, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB)
-cgemm_t5_kernel(int m, int k, int N, int tmem_cols, int lbo_pad, int64_t n, c64 alpha, const c64 *__restrict__ Mp, int64_t sa_i,
-                int64_t sa_l, int conjA, const float *__restrict__ X, int64_t ldx2, c64 beta, int beta_zero,
-                float *__restrict__ Y, int64_t ldy2) {
+template <int NCH>
+__global__ void __launch_bounds__(WS_THREADS, 1)
+cgemm_t5ws_kernel(int m, int k, int N, int tmem_cols, int lbo_pad, int ns, int64_t n, c64 alpha, const c64 *__restrict__ Mp, int64_t sa_i,
+                  int64_t sa_l, int conjA, const float *__restrict__ X, int64_t ldx2, c64 beta, int beta_zero,
+                  float *__restrict__ Y, int64_t ldy2) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) WsBars bars;
     __shared__ uint32_t tmem_slot;
     Ctx c;
     const int K2 = 2 * k;
     c.X = X; c.ldx2 = ldx2; c.n = n; c.ntiles = (n + ROWS - 1) / ROWS;
     c.KCH = K2 / NCH; c.CPR = c.KCH / 4;
     c.lbo_a = ROWS * 16 + lbo_pad; c.lbo_b = (uint32_t)(2 * N) * 16;
+    const uint32_t stage_bytes = 2u * (uint32_t)c.CPR * c.lbo_a;
     c.a_hi = smem; c.a_lo = c.a_hi + (size_t)c.CPR * c.lbo_a;
-    c.b_cat = c.a_lo + (size_t)c.CPR * c.lbo_a;
-    c.bar = &bar;
-    // instruction descriptor: fp32 accumulate (bit 4), TF32 A and B (bits 7, 10), both K-major, N >> 3 at 17, M >> 4 at 24
+    c.b_cat = smem + (size_t)ns * stage_bytes;
     c.idesc_hi = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
     c.idesc_cat = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * N) >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
 #pragma unroll
     for (int it = 0; it < RPT; ++it) {
-        const int q = it * THREADS + threadIdx.x, r = q / c.CPR;
-        c.rc[it] = (uint32_t)(r & 255) | ((uint32_t)(q - r * c.CPR) << 8);
+        const int q = it * THREADS + (threadIdx.x & (THREADS - 1)), r = q / c.CPR, sl = q - r * c.CPR;
+        c.rrow[it] = r;
+        c.goff[it] = (int64_t)r * ldx2 + 4 * sl;
+        c.soff[it] = q < ROWS * c.CPR ? (uint32_t)sl * c.lbo_a + (uint32_t)r * 16 : 0xFFFFFFFFu;
     }
-    // alpha*op(M)' as stacked (hi, lo) TF32 planes: element (o, kf) at (kf/4)*LBO_B + (o | o + N)*16 + (kf%4)*4
-    for (int e = threadIdx.x; e < N * K2; e += THREADS) {
+    for (int e = threadIdx.x; e < N * K2; e += WS_THREADS) {
         const int kf = e % K2, o = e / K2, i = o >> 1, l = kf >> 1;
         float v = 0.f;
         if (i < m) {
@@ -465,7 +441,8 @@ cgemm_t5_kernel(int m, int k, int N, int tmem_cols, int lbo_pad, int64_t n, c64 
     }
     fence_async_smem();
     if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar)) : "memory");
+        for (int s = 0; s < WS_MAX_STAGES; ++s) { mbar_init(&bars.full[s], THREADS); mbar_init(&bars.empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&bars.tfull[s], 1); mbar_init(&bars.tempty[s], WS_EPI); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 32) {
@@ -477,27 +454,96 @@ cgemm_t5_kernel(int m, int k, int N, int tmem_cols, int lbo_pad, int64_t n, c64 
     fence_after();
     c.tmem = tmem_slot;
 
-    uint32_t phase = 0;
-    const int64_t stride = gridDim.x;
-    int64_t tile = blockIdx.x;
-    float4 rb0[RPT], rb1[RPT];
-    if (NCH == 2) {
-        load_chunk(rb0, c, tile, 0);
-        load_chunk(rb1, c, tile, 1);
-        for (; tile < c.ntiles; tile += stride) {
-            step(rb0, c, 0, true, tile + stride, 0, phase);
-            step(rb1, c, 1, false, tile + stride, 1, phase);
-            epilogue(c, tile, N, m, beta, beta_zero, Y, ldy2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t ntl = (int64_t)blockIdx.x < c.ntiles ? (c.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // tiles of this CTA
+    const int64_t nsteps = ntl * NCH;
+    if (warp < WS_CONV / 32) {
+        // ---------------- converters
+        // two groups of 8 warps take alternate chunks, so that the wait -> split -> fence -> arrive chain of one chunk
+        // overlaps the other group's; two chunks of loads in flight per group (96 KB per SM)
+        const int grp = warp / (THREADS / 32);
+        float4 rbA[RPT], rbB[RPT];
+#define IB200_WS_LOAD(RB, Q) load_chunk(RB, c, (int64_t)blockIdx.x + ((Q) / NCH) * (int64_t)gridDim.x, (int)((Q) % NCH))
+        int64_t q = grp;
+        IB200_WS_LOAD(rbA, q); IB200_WS_LOAD(rbB, q + 2);
+        Ring ring; ring.s = grp; ring.ns = ns; ring.ph = 0;
+        for (; q < nsteps; q += 4) {
+            ws_convert(rbA, c, bars, stage_bytes, ring); ring.advance(2);
+            IB200_WS_LOAD(rbA, q + 4);
+            if (q + 2 < nsteps) { ws_convert(rbB, c, bars, stage_bytes, ring); ring.advance(2); IB200_WS_LOAD(rbB, q + 6); }
+        }
+#undef IB200_WS_LOAD
+    } else if (warp < (WS_CONV + WS_EPI) / 32) {
+        // ---------------- epilogue: TMEM (lane = column of X, column = real output | + N: the hi*lo half) -> Y
+        const int quarter = warp & 3;
+        for (int64_t i = 0; i < ntl; ++i) {
+            const int a = (int)(i & 1);
+            const int64_t tile = (int64_t)blockIdx.x + i * (int64_t)gridDim.x, col = tile * ROWS + quarter * 32 + lane;
+            mbar_wait(&bars.tfull[a], (uint32_t)((i >> 1) & 1));
+            fence_after();
+            for (int cb = 0; cb < 2 * m; cb += 16) {
+                uint32_t v[16], w[16];
+                const uint32_t taddr = c.tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * 2 * N + cb);
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                             : "r"(taddr));
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                             : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
+                               "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+                             : "r"(taddr + (uint32_t)N));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (cb + 16 >= 2 * m) {                                // last block read: the accumulator stage is free again
+                    fence_before();
+                    mbar_arrive(&bars.tempty[a]);
+                }
+                if (col < n) {
+                    float *yp = Y + col * ldy2 + cb;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int ii = cb / 2 + 2 * j;
+                        c64 r0 = mk(__uint_as_float(v[4 * j]) + __uint_as_float(w[4 * j]), __uint_as_float(v[4 * j + 1]) + __uint_as_float(w[4 * j + 1]));
+                        c64 r1 = mk(__uint_as_float(v[4 * j + 2]) + __uint_as_float(w[4 * j + 2]), __uint_as_float(v[4 * j + 3]) + __uint_as_float(w[4 * j + 3]));
+                        if (ii + 1 < m) {
+                            if (!beta_zero) {
+                                const float4 o = *reinterpret_cast<const float4 *>(yp + 4 * j);
+                                r0 = cfma(beta, mk(o.x, o.y), r0); r1 = cfma(beta, mk(o.z, o.w), r1);
+                            }
+                            __stcs(reinterpret_cast<float4 *>(yp + 4 * j), make_float4(r0.x, r0.y, r1.x, r1.y));
+                        } else if (ii < m) {
+                            if (!beta_zero) r0 = cfma(beta, *reinterpret_cast<const c64 *>(yp + 4 * j), r0);
+                            __stcs(reinterpret_cast<c64 *>(yp + 4 * j), r0);
+                        }
+                    }
+                }
+            }
         }
     } else {
-        load_chunk(rb0, c, tile, 0);
-        load_chunk(rb1, c, tile + stride, 0);
-        for (; tile < c.ntiles; tile += 2 * stride) {
-            step(rb0, c, 0, true, tile + 2 * stride, 0, phase);
-            epilogue(c, tile, N, m, beta, beta_zero, Y, ldy2);
-            if (tile + stride < c.ntiles) {                // block-uniform
-                step(rb1, c, 0, true, tile + 3 * stride, 0, phase);
-                epilogue(c, tile + stride, N, m, beta, beta_zero, Y, ldy2);
+        // ---------------- MMA warp: lane 0 issues, the warp waits together
+        const uint32_t ah0 = smem_u32(c.a_hi), al0 = smem_u32(c.a_lo), bc = smem_u32(c.b_cat);
+        Ring ring; ring.s = 0; ring.ns = ns; ring.ph = 0;
+        for (int64_t i = 0; i < ntl; ++i) {
+            const int a = (int)(i & 1);
+            mbar_wait(&bars.tempty[a], (uint32_t)((i >> 1) & 1) ^ 1u);  // epilogue has drained this accumulator stage
+            for (int ch = 0; ch < NCH; ++ch) {
+                const int s = ring.s;
+                mbar_wait(&bars.full[s], ring.ph);
+                fence_after();
+                if (lane == 0) {
+                    const uint32_t tm = c.tmem + (uint32_t)(a * 2 * N);
+                    for (int ks = 0; ks < c.KCH / 8; ++ks) {
+                        const uint32_t ao = (uint32_t)s * stage_bytes + (uint32_t)(2 * ks) * c.lbo_a;
+                        const uint32_t bo = (uint32_t)(ch * c.CPR + 2 * ks) * c.lbo_b;
+                        const uint64_t dah = make_desc(ah0 + ao, c.lbo_a, 128), dal = make_desc(al0 + ao, c.lbo_a, 128);
+                        const uint64_t db = make_desc(bc + bo, c.lbo_b, 128);
+                        mma_ss(tm, dah, db, c.idesc_cat, (ch == 0 && ks == 0) ? 0u : 1u);
+                        mma_ss(tm, dal, db, c.idesc_hi, 1u);
+                    }
+                    commit(&bars.empty[s]);                            // operand stage free when these MMAs have read it
+                    if (ch == NCH - 1) commit(&bars.tfull[a]);         // accumulator complete
+                }
+                __syncwarp();
+                ring.advance(1);
             }
         }
     }
@@ -510,9 +556,10 @@ cgemm_t5_kernel(int m, int k, int N, int tmem_cols, int lbo_pad, int64_t n, c64 
 
 static int g_t5_pad = -1;             // IB200_T5_PAD: bytes added to the k-slice stride of the X operand planes (bank spread)
 
-static size_t t5_smem(int64_t m, int64_t k, int pad) {
+// ns (hi, lo) operand stages + stacked op(M)' planes
+static size_t t5_smem(int64_t m, int64_t k, int pad, int ns) {
     const int64_t K2 = 2 * k, nch = K2 <= t5::KCH_MAX ? 1 : 2, cpr = K2 / nch / 4, N = (2 * m + 31) / 32 * 32;
-    return (size_t)(2 * cpr * (t5::ROWS * 16 + pad) + 2 * (K2 / 4) * N * 16);
+    return (size_t)(ns * 2 * cpr * (t5::ROWS * 16 + pad) + 2 * (K2 / 4) * N * 16);
 }
 
 // tcgen05 path: op(M) with <= 64 rows, k a multiple of 4 (8 when two chunks are needed) up to 48, X and Y columns 16-byte aligned
@@ -520,7 +567,7 @@ static bool t5_applicable(int64_t m, int64_t n, int64_t k, const c64 *B, int64_t
     if (sb_l != 1 || m < 1 || m > 64 || k < 4 || k > 48 || (k & 3) || n < 128) return false;
     if (2 * k > t5::KCH_MAX && (k & 7)) return false;
     if ((reinterpret_cast<uintptr_t>(B) & 15) || (sb_j & 1) || (reinterpret_cast<uintptr_t>(C) & 15) || (ldc & 1)) return false;
-    return t5_smem(m, k, 128) <= 100 * 1024;
+    return t5_smem(m, k, 128, 2) <= 200 * 1024;
 }
 
 static int launch_t5(cudaStream_t s, int64_t m, int64_t n, int64_t k, c64 alpha, const c64 *A, int64_t sa_i, int64_t sa_l,
@@ -531,26 +578,24 @@ static int launch_t5(cudaStream_t s, int64_t m, int64_t n, int64_t k, c64 alpha,
         IB200_REQUIRE(g_t5_pad >= 0 && g_t5_pad <= 128 && g_t5_pad % 16 == 0, "IB200_T5_PAD is a multiple of 16 up to 128");
     }
     const int N = (int)((2 * m + 31) / 32 * 32);
-    const int tmem_cols = N <= 32 ? 64 : N <= 64 ? 128 : 256;          // accumulator 128 x 2N (hi*hi + lo*hi | hi*lo)
-    const size_t smem = t5_smem(m, k, g_t5_pad);
     const int nch = 2 * k <= t5::KCH_MAX ? 1 : 2;
-    static int minb = -1;
-    if (minb < 0) { const char *e = getenv("IB200_T5_MINB"); minb = (e && atoi(e) == 3) ? 3 : 2; }
-    auto kern = nch == 1 ? (minb == 3 ? t5::cgemm_t5_kernel<1, 3> : t5::cgemm_t5_kernel<1, 2>)
-                         : (minb == 3 ? t5::cgemm_t5_kernel<2, 3> : t5::cgemm_t5_kernel<2, 2>);
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[nch - 1]) {
-        IB200_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(100 * 1024)));
-        attr_set[nch - 1] = true;
+    static int ns_env = -1;
+    if (ns_env < 0) { const char *e = getenv("IB200_T5_STAGES"); ns_env = e ? atoi(e) : 0; }
+    int ns = 2;                                            // operand stages: two measured fastest (12 x 48: 1.29 ms against 1.51 ms with three)
+    if (ns_env > 2 && ns_env <= t5::WS_MAX_STAGES && t5_smem(m, k, g_t5_pad, ns_env) <= 200 * 1024) ns = ns_env;
+    const size_t smem = t5_smem(m, k, g_t5_pad, ns);
+    const int need = 4 * N, tmem_cols = need <= 128 ? 128 : need <= 256 ? 256 : 512;    // two accumulator stages of 2N columns
+    auto kern = nch == 1 ? t5::cgemm_t5ws_kernel<1> : t5::cgemm_t5ws_kernel<2>;
+    static bool attr_ws[2] = {false, false};
+    if (!attr_ws[nch - 1]) {
+        IB200_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+        attr_ws[nch - 1] = true;
     }
-    int64_t per_sm = (int64_t)(228 * 1024) / (int64_t)(smem + 1280);
-    if (per_sm > 4) per_sm = 4;
-    if (per_sm < 1) per_sm = 1;
     int64_t grid = ceil_div(n, t5::ROWS);
-    if (grid > per_sm * sm_count()) grid = per_sm * sm_count();
-    kern<<<(unsigned)grid, t5::THREADS, smem, s>>>((int)m, (int)k, N, tmem_cols, g_t5_pad, n, alpha, A, sa_i, sa_l, conjA,
-                                                   (const float *)B, 2 * ldb, beta, (beta.x == 0.f && beta.y == 0.f) ? 1 : 0,
-                                                   (float *)C, 2 * ldc);
+    if (grid > sm_count()) grid = sm_count();                                           // one persistent CTA per SM
+    kern<<<(unsigned)grid, t5::WS_THREADS, smem, s>>>((int)m, (int)k, N, tmem_cols, g_t5_pad, ns, n, alpha, A, sa_i, sa_l, conjA,
+                                                      (const float *)B, 2 * ldb, beta, (beta.x == 0.f && beta.y == 0.f) ? 1 : 0,
+                                                      (float *)C, 2 * ldc);
     IB200_LAUNCH_CHECK();
     return 0;
 }

@@ -67,7 +67,7 @@ def main():
     print("|---|---|---:|---:|---:|---:|")
     for label, fn in (("Y(12 x n) = M X  (compression)", lambda: B.cgemm(yd, Md, xd, 1.0, 0.0, forward=True)),
                       ("Z(48 x n) = M^H Y (expansion)", lambda: B.cgemm(zd, Md, yd, 1.0, 0.0, forward=False))):
-        for mode, name in ((0, "mma.sync, 3xTF32 (cgemm_tc_kernel; default)"), (3, "tcgen05 + TMEM, 3xTF32 (cgemm_t5_kernel)"), (1, "SIMT fp32 (cgemm_kernel)")):
+        for mode, name in ((0, "mma.sync, 3xTF32 (cgemm_tc_kernel; default)"), (3, "tcgen05 + TMEM, warp-specialised, 3xTF32 (cgemm_t5ws_kernel)"), (1, "SIMT fp32 (cgemm_kernel)")):
             if str(mode) not in args.modes.split(","):
                 continue
             B._lib.cgemm_mode(mode)
