@@ -104,3 +104,67 @@ def test_split_tf32_bit_trick():
     lo_t = (lo.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)                           # operand as the MMA reads it
     err = np.abs(x.astype(np.float64) - hi.astype(np.float64) - lo_t.astype(np.float64))
     assert np.all(err <= np.abs(x.astype(np.float64)) * 2.0 ** -21)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# tcgen05 kernel (cgemm_t5ws_kernel): shared-memory operand layout and descriptor arithmetic.  The model of the
+# hardware side is the canonical K-major no-swizzle layout of a shared-memory matrix descriptor (8-row x 16-byte
+# core matrices; SBO bytes between 8-row groups, LBO bytes between the two 16-byte k slices of one K = 8 MMA), which
+# is what the kernel's descriptors (start, LBO, SBO = 128) claim; GPU parity tests confirm the claim on hardware.
+def _mma_read(plane, start, lbo, sbo, rows):
+    """rows x 8 operand an MMA fetches through descriptor (start, lbo, sbo); plane is a float32 array, bytes / 4."""
+    out = np.zeros((rows, 8))
+    for r in range(rows):
+        for kk in range(8):
+            out[r, kk] = plane[(start + (r // 8) * sbo + (r % 8) * 16 + (kk // 4) * lbo + (kk % 4) * 4) // 4]
+    return out
+
+
+def _split(x):
+    hi = np.round(x * 2.0 ** 10 / 2.0 ** np.floor(np.log2(np.maximum(np.abs(x), 1e-300)))) \
+        * 2.0 ** np.floor(np.log2(np.maximum(np.abs(x), 1e-300))) / 2.0 ** 10
+    return hi, x - hi
+
+
+@pytest.mark.parametrize("m,k", [(12, 48), (48, 12), (5, 8), (20, 40)])
+def test_t5_operand_layout(m, k):
+    rs = np.random.RandomState(k)
+    ROWS, pad = 128, 16
+    K2 = 2 * k
+    NCH = 1 if K2 <= 48 else 2
+    KCH, N = K2 // NCH, (2 * m + 31) // 32 * 32
+    CPR, lbo_a, lbo_b = KCH // 4, ROWS * 16 + pad, 2 * N * 16
+    M = rs.randn(m, k) + 1j * rs.randn(m, k)
+    X = rs.randn(k, ROWS) + 1j * rs.randn(k, ROWS)
+    alpha = 1.25 + 0.5j
+    Xf = np.zeros((ROWS, K2)); Xf[:, 0::2], Xf[:, 1::2] = X.real.T, X.imag.T
+    # stacked planes of alpha*M' as the kernel writes them
+    bcat = np.zeros((K2 // 4) * lbo_b // 4)
+    for o in range(N):
+        for kf in range(K2):
+            i, l, v = o >> 1, kf >> 1, 0.0
+            if i < m:
+                w = alpha * M[i, l]
+                v = (w.real if kf & 1 else w.imag) if o & 1 else (-w.imag if kf & 1 else w.real)
+            h, lo = _split(np.array([v]))
+            off = (kf >> 2) * lbo_b + o * 16 + (kf & 3) * 4
+            bcat[off // 4], bcat[(off + N * 16) // 4] = h[0], lo[0]
+    D = np.zeros((ROWS, 2 * N))                                # TMEM accumulator: lane = column of X
+    for ch in range(NCH):
+        a_hi, a_lo = np.zeros(CPR * lbo_a // 4), np.zeros(CPR * lbo_a // 4)
+        for q in range(ROWS * CPR):                            # converter pieces: q -> (r, slice)
+            r, sl = q // CPR, q % CPR
+            h, lo = _split(Xf[r, ch * KCH + 4 * sl: ch * KCH + 4 * sl + 4])
+            off = (sl * lbo_a + r * 16) // 4
+            a_hi[off:off + 4], a_lo[off:off + 4] = h, lo
+        for ks in range(KCH // 8):
+            ao, bo = 2 * ks * lbo_a, (ch * CPR + 2 * ks) * lbo_b
+            Ah, Al = _mma_read(a_hi, ao, lbo_a, 128, ROWS), _mma_read(a_lo, ao, lbo_a, 128, ROWS)
+            Bc = _mma_read(bcat, bo, lbo_b, 128, 2 * N)
+            D += Ah @ Bc.T                                     # 128 x 2N: hi*hi | hi*lo
+            D[:, :N] += Al @ Bc[:N].T                          # 128 x N : lo*hi
+    Yf = D[:, :N] + D[:, N:]
+    got = (Yf[:, 0:2 * m:2] + 1j * Yf[:, 1:2 * m:2]).T
+    want = alpha * (M @ X)
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-5
+    assert np.all(Yf[:, 2 * m:] == 0)
