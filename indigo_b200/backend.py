@@ -349,6 +349,13 @@ def make_backend_class(Base, name="B200Backend"):
             return self.dndarray(self, pinned.shape, pinned.dtype, own=False,
                                  data=DevPtr(pinned.ctypes.data, keep=pinned), name='mapped')
 
+        def NUFFT(self, M, N, coord, width=3, n=128, oversamp=None, dtype=_C64, **kwargs):
+            """Backend.NUFFT (backend.py:393-450) unchanged; the returned product remembers its arguments so that
+            indigo_b200.fused.fuse_transform can swap the SENSE tree it ends up in for the fused node."""
+            from .fused import tag_nufft
+            op = super().NUFFT(M, N, coord, width=width, n=n, oversamp=oversamp, dtype=dtype, **kwargs)
+            return tag_nufft(op, N, coord, width, n, oversamp)
+
         def barrier(self):
             self._lib.stream_sync(self._stream)
 

@@ -329,3 +329,96 @@ def sense_operator_fused(B, N, coord, maps, oversamp=2.0, weights=None, width=3,
     Fwd, _ = _cache[ops]
     dev = SenseDevice(B, N, coord, maps, oversamp, weights, width, n)
     return Fwd(B, dev)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# The fusion as a Transform ("a new visitor in the style of pics.py:104-177 /
+# transforms.py:202-249"): trees built by the unchanged recipe of examples/pics.py:92-95,
+#     A = KronI(C, [Diag(dcf) *] B.NUFFT(M, N, coord)) * VStack_c Diag(maps_c),
+# are recognised and replaced by the fused node; anything else is left as it is.  The interpolation matrix
+# alone does not determine the trajectory, so B200Backend.NUFFT tags the product it returns with the
+# arguments it was built from (`tag_nufft`); maps and row weights are read back from the diagonal matrices.
+def tag_nufft(op, N, coord, width, n, oversamp):
+    op._b200_nufft = dict(N=tuple(int(v) for v in N), coord=np.asarray(coord), width=width, n=n, oversamp=oversamp)
+    return op
+
+
+def _diagonal_of(node):
+    """Diagonal of an SpMatrix node that holds a square diagonal matrix, else None."""
+    if type(node).__name__ != 'SpMatrix':
+        return None
+    M = node._matrix
+    if M.shape[0] != M.shape[1] or M.nnz > M.shape[0]:
+        return None
+    coo = M.tocoo()
+    if not np.array_equal(coo.row, coo.col):
+        return None
+    return np.asarray(M.diagonal())
+
+
+def match_sense_tree(node):
+    """Arguments of the SENSE operator a Product node was built from (dict with N, coord, maps, weights, oversamp,
+    width, n), or None when the node is not KronI(C, [Diag *] NUFFT) * VStack(Diag...)."""
+    if type(node).__name__ != 'Product':
+        return None
+    kids = node.children
+    if len(kids) != 2 or type(kids[0]).__name__ != 'Kron' or type(kids[1]).__name__ != 'VStack':
+        return None
+    eye, F1 = kids[0].children
+    if type(eye).__name__ != 'Eye':
+        return None
+    C = int(eye.shape[0])
+    weights, meta = None, getattr(F1, '_b200_nufft', None)
+    if meta is None and type(F1).__name__ == 'Product' and len(F1.children) == 2:
+        D, F2 = F1.children
+        meta, weights = getattr(F2, '_b200_nufft', None), _diagonal_of(D)
+        if meta is None or weights is None:
+            return None
+    if meta is None:
+        return None
+    N = meta['N']
+    nvox = int(np.prod(N))
+    coils = kids[1].children
+    if len(coils) != C:
+        return None
+    cols = []
+    for ch in coils:
+        d = _diagonal_of(ch)
+        if d is None or d.shape[0] != nvox:
+            return None
+        cols.append(d.astype(_C64))
+    maps = np.stack(cols, axis=1).reshape(tuple(N) + (C,), order='F')
+    if weights is not None:
+        if np.abs(np.imag(weights)).max() > 0:
+            return None                                    # complex row weights are not a density compensation
+        weights = np.real(weights).astype(np.float32)
+    return dict(N=N, coord=meta['coord'], maps=maps, weights=weights, oversamp=meta['oversamp'],
+                width=meta['width'], n=meta['n'])
+
+
+def fuse_transform(B):
+    """Transform class of B's operator family whose visit() swaps recognised SENSE trees for the fused node:
+        A = A.optimize([fuse_transform(B)])        # or: sense_operator(B, ..., recipe=[fuse_transform(B)])
+    Grids without specialised passes (RuntimeError from the plan) keep their tree."""
+    ops = getattr(B, 'ops', None)
+    if ops is not None and ops.__name__.startswith('indigo_b200'):
+        from .host.rewrites import Transform
+    else:
+        from indigo.transforms import Transform
+
+    class FuseSenseNUFFT(Transform):
+        build = staticmethod(lambda backend, **kw: sense_operator_fused(backend, kw['N'], kw['coord'], kw['maps'], kw['oversamp'],
+                                                                        kw['weights'], kw['width'], kw['n']))
+
+        def visit_Product(self, node):
+            hit = match_sense_tree(node)
+            if hit is None:
+                return self.generic_visit(node)
+            try:
+                fused = type(self).build(node._backend, **hit)
+            except RuntimeError:
+                return self.generic_visit(node)
+            fused._name = (getattr(node, '_name', '') or 'SENSE1') + '.fused'
+            return fused
+
+    return FuseSenseNUFFT

@@ -208,3 +208,28 @@ def test_fused_refuses_unsupported_grid(B):
     rs, coord, maps, w = _setup(N, C, "random", False)
     with pytest.raises(RuntimeError):
         sense_operator_fused(B, N, coord, maps, 2.0)
+
+
+def test_fuse_transform_swaps_the_pics_tree(B):
+    """The tree of examples/pics.py:92-95 built by the unchanged builders (B.NUFFT, B.KronI, B.VStack, B.Diag) and
+    handed to the fusion Transform comes back as the fused node and matches the oracle; a grid without
+    specialised passes keeps its tree and still evaluates (six-call path)."""
+    from indigo_b200.fused import fuse_transform
+    from indigo_b200.sense import sense_operator
+    N, C = (16, 16, 16), 4
+    rs, coord, maps, w = _setup(N, C, "koosh", True)
+    A = sense_operator(B, N, coord, maps, 2.0, weights=w, recipe=[fuse_transform(B)])
+    assert type(A).__name__ == "FusedSenseNUFFT"
+    ref = osense.SenseOperator(N, coord, maps, 2.0, weights=w)
+    x = synth.rand64c(rs, int(np.prod(N)), 1)
+    y = synth.rand64c(rs, ref.M * C, 1)
+    assert relerr(A * x, ref.forward(x)) < TOL
+    assert relerr(A.H * y, ref.adjoint(y)) < TOL
+    assert relerr(normal_operator(A) * x, ref.normal(x)) < TOL
+    N2 = (11, 12, 13)                                # 22 x 24 x 26 grid: no fused plan
+    rs2, coord2, maps2, _ = _setup(N2, 2, "random", False)
+    A2 = sense_operator(B, N2, coord2, maps2, 2.0, recipe=[fuse_transform(B)])
+    assert type(A2).__name__ == "Product"
+    ref2 = osense.SenseOperator(N2, coord2, maps2, 2.0)
+    x2 = synth.rand64c(rs2, int(np.prod(N2)), 1)
+    assert relerr(A2 * x2, ref2.forward(x2)) < TOL
