@@ -232,12 +232,15 @@ int ib200_csr_transpose_conj(void *stream, int64_t m, int64_t k, int64_t nnz,
                              void *t_vals, int32_t *t_colind, int32_t *t_rowptr, int32_t *work,
                              const int32_t *colrank);
 /* Backend.cdiamm, backend.py:521-526 (oracle np.py:129-136; _customgpu.cu:83-143).
- * A is m x k in DIA form; data is (ncolsA x noffsets) column-major where
- * ncolsA = k, i.e. scipy's dia.data transposed (backend.py:610).
+ * A is m x k in DIA form; data is (data_cols x noffsets) column-major with column pitch
+ * data_pitch, i.e. scipy's dia.data transposed (backend.py:610).  scipy does not promise
+ * data_cols == k (todia() gives max column + 1, diags() can be wider): entry (d, j) is the value
+ * in column j of diagonal d, columns >= data_cols hold nothing.
  *   adjoint == 0 : Y(m x n) = alpha*A*X(k x n) + beta*Y
  *   adjoint != 0 : Y(k x n) = alpha*A^H*X(m x n) + beta*Y */
 int ib200_cdiamm(void *stream, int adjoint, int64_t m, int64_t k, int64_t ncols, int64_t noffsets,
-                 const int32_t *offsets, const void *data, float alpha_re, float alpha_im,
+                 const int32_t *offsets, const void *data, int64_t data_cols, int64_t data_pitch,
+                 float alpha_re, float alpha_im,
                  const void *X, int64_t ldx, float beta_re, float beta_im, void *Y, int64_t ldy);
 /* Backend.onemm, backend.py:528-533 (oracle np.py:95-97; _customgpu.cu:15-47):
  * Y(m x n) = beta*Y + alpha * ones(m,k) * X(k x n). */

@@ -64,7 +64,7 @@ SIGNATURES = {
     "ib200_kb_fill": (_i, [_vp, _i64, _vp, POINTER(_i64), c_double, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "ib200_sense_ph_count": (_i, [_vp, _i64, _i, _vp, _vp, _vp]),
     "ib200_sense_ph_fill": (_i, [_vp, _i64, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "ib200_cdiamm": (_i, [_vp, _i, _i64, _i64, _i64, _i64, _vp, _vp, _f, _f, _vp, _i64, _f, _f, _vp, _i64]),
+    "ib200_cdiamm": (_i, [_vp, _i, _i64, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _f, _f, _vp, _i64, _f, _f, _vp, _i64]),
     "ib200_onemm": (_i, [_vp, _i64, _i64, _i64, _f, _f, _vp, _i64, _f, _f, _vp, _i64]),
     "ib200_fmax": (_i, [_vp, _i64, _f, _vp]),
     "ib200_fft_plan_create": (_i, [POINTER(_vp), _i, POINTER(_i64), _i64]),

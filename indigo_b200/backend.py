@@ -7,9 +7,11 @@ Drop-in boundary.  The class is produced by
   * Base = indigo.backends.backend.Backend when the reference package is
     importable (indigo_b200.register() then exposes it as get_backend('b200')),
     so trees built by the reference's own operators.py / transforms.py run
-    unchanged;
-  * Base = indigo_b200.host.HostBackend (our mirror of that interface) on
-    machines without the reference, e.g. the GPU box.
+    unchanged -- tests/test_gpu_reference.py does exactly that, and runs the
+    reference's own test_backends.py / test_operators.py on this backend;
+  * Base = indigo_b200.standalone.StandaloneBase on machines without the
+    reference (the GPU box): arrays, primitives, cg, the fused SENSE node and the
+    direct six-call operator, no operator tree.
 Every method below replaces one abstract method of the reference
 (backend.py:453-533) or one hook of its device array (backend.py:180-220) and
 ends in exactly one C-ABI call; PyTorch only owns the device buffers and the
@@ -23,7 +25,7 @@ import numpy as np
 import scipy.sparse as spp
 
 from . import _lib
-from .host.hostbackend import HostBackend
+from .standalone import StandaloneBase
 
 log = logging.getLogger(__name__)
 _C64 = np.dtype('complex64')
@@ -45,7 +47,8 @@ def _re_im(v):
 
 
 def make_backend_class(Base, name="B200Backend"):
-    """Builds the backend class on top of `Base` (the reference's Backend or our mirror)."""
+    """Builds the backend class on top of `Base`: the reference's `indigo.backends.backend.Backend`, or
+    indigo_b200.standalone.StandaloneBase when the reference is not installed."""
 
     class B200Array(Base.dndarray):
         """Column-major device array; pointer model of the reference's CUDA array
@@ -154,28 +157,67 @@ def make_backend_class(Base, name="B200Backend"):
                 return [(self.ptr, int(self.size))]
             return [(self.ptr + c * self.ld * it, int(self.shape[0])) for c in range(self.shape[1])]
 
-    class B200Csr(Base.csr_matrix):
-        """Device CSR with a device-side inspector and, for matrices whose adjoint is a
-        scatter with collisions, a stored conjugate transpose so that A^H x is a gather
-        (replaces the atomic path of _customcpu.c:49-79 / cusparse's transpose mode).
-        User-visible rowPtrs/colInds/values stay bit-identical to the reference's."""
+    class B200Csr(object):
+        """Device CSR holder of Backend.csr_matrix (backend.py:535-596) with a device-side inspector and, for
+        matrices whose adjoint is a scatter with collisions, a stored conjugate transpose so that A^H x is a
+        gather (replaces the atomic path of _customcpu.c:49-79 / cusparse's transpose mode).
+        User-visible rowPtrs/colInds/values stay bit-identical to the reference's, index dtype included:
+        scipy switches to int64 when a dimension or nnz reaches 2^31 (cfg4's P on one GPU has 2.3 G columns);
+        such a matrix is additionally held as column blocks of fewer than `max_block_cols` columns with
+        int32 local indices, and a product is the sum / concatenation of the block products."""
         _index_base = 0
+        max_block_cols = (1 << 31) - 1024
 
         def __init__(self, backend, A, name='mat'):
             if not isinstance(A, spp.csr_matrix):
                 A = A.tocsr()
             A = self._type_correct(A)
-            if A.indices.dtype != np.int32 or A.indptr.dtype != np.int32:
-                raise ValueError("b200 backend supports int32 CSR indices only (matrix %s has %s); "
-                                 "split the operator (SURVEY.md 8a, cfg4 note)" % (name, A.indices.dtype))
             self._backend = backend
             self._name = name
+            self.shape, self.dtype = A.shape, A.dtype
+            self._adj = None
+            self._blocks = None
+            wide = A.indices.dtype != np.int32 or A.indptr.dtype != np.int32 or A.shape[1] > self.max_block_cols
+            if wide:
+                if A.nnz >= (1 << 31):
+                    raise ValueError("b200 backend holds at most 2^31-1 stored entries per matrix (matrix %s has %d); "
+                                     "split the operator (SURVEY.md 8a, cfg4 note)" % (name, A.nnz))
+                self.rowPtrs = backend.copy_array(A.indptr, name=name + ".rowPtrs")
+                self.colInds = backend.copy_array(A.indices, name=name + ".colInds")
+                self.values = backend.copy_array(A.data, name=name + ".data")
+                self._split_columns(A)
+                return
             self.rowPtrs = backend.copy_array(A.indptr, name=name + ".rowPtrs")
             self.colInds = backend.copy_array(A.indices, name=name + ".colInds")
             self.values = backend.copy_array(A.data, name=name + ".data")
-            self.shape, self.dtype = A.shape, A.dtype
-            self._adj = None
             self._inspect_device()
+
+        def _type_correct(self, A):
+            return A.astype(np.complex64)
+
+        nbytes = property(lambda self: self.rowPtrs.nbytes + self.colInds.nbytes + self.values.nbytes)
+        nnz = property(lambda self: self.values.size)
+
+        def _split_columns(self, A):
+            """Column blocks [c0, c1) of a matrix with 64-bit indices, each a B200Csr of its own with int32 indices
+            (`A x = sum_b A_b x[c0:c1]`, `(A^H y)[c0:c1] = A_b^H y`); the inspector's figures are combined."""
+            k, step = A.shape[1], int(self.max_block_cols)
+            self._blocks = []
+            nzcols, exw, nzrows = 0, 1, np.zeros(A.shape[0], dtype=bool)
+            for c0 in range(0, k, step):
+                c1 = min(k, c0 + step)
+                sub = A[:, c0:c1].tocsr()
+                sub.sort_indices()
+                sub = spp.csr_matrix((sub.data, sub.indices.astype(np.int32), sub.indptr.astype(np.int32)),
+                                     shape=sub.shape)
+                blk = type(self)(self._backend, sub, name="%s[:, %d:%d]" % (self._name, c0, c1))
+                self._blocks.append((c0, c1, blk))
+                nzcols += int(round(blk._col_frac * (c1 - c0)))
+                exw &= blk._exwrite
+                nzrows |= np.diff(sub.indptr) > 0
+            self._row_frac = float(nzrows.sum()) / A.shape[0] if A.shape[0] else 1.0
+            self._col_frac = nzcols / k if k else 1.0
+            self._exwrite = int(exw)
 
         @classmethod
         def from_device(cls, backend, shape, rowPtrs, colInds, values, name='mat'):
@@ -186,6 +228,7 @@ def make_backend_class(Base, name="B200Backend"):
             self.rowPtrs, self.colInds, self.values = rowPtrs, colInds, values
             self.shape, self.dtype = tuple(int(v) for v in shape), _C64
             self._adj = None
+            self._blocks = None
             self._inspect_device()
             return self
 
@@ -276,6 +319,10 @@ def make_backend_class(Base, name="B200Backend"):
             assert x.dtype == _C64, "Bad dtype: expected compelx64, got %s" % x.dtype
             assert y.dtype == _C64, "Bad dtype: expected compelx64, got %s" % y.dtype
             assert self.values.dtype == _C64
+            if self._blocks is not None:
+                for i, (c0, c1, blk) in enumerate(self._blocks):
+                    blk.forward(y, x[c0:c1, :], alpha=alpha, beta=beta if i == 0 else 1)
+                return
             if self._packed_product('fwd', y, x, alpha, beta):
                 return
             self._backend.ccsrmm(y, self.shape, self.colInds, self.rowPtrs, self.values, x, alpha=alpha, beta=beta,
@@ -286,6 +333,10 @@ def make_backend_class(Base, name="B200Backend"):
             assert y.dtype == _C64, "Bad dtype: expected compelx64, got %s" % y.dtype
             assert self.values.dtype == _C64
             b = self._backend
+            if self._blocks is not None:
+                for c0, c1, blk in self._blocks:
+                    blk.adjoint(y[c0:c1, :], x, alpha=alpha, beta=beta)
+                return
             if self._exwrite or not self._use_stored_adjoint():
                 return b.ccsrmm(y, self.shape, self.colInds, self.rowPtrs, self.values, x,
                                 alpha=alpha, beta=beta, adjoint=True, exwrite=self._exwrite)
@@ -315,10 +366,25 @@ def make_backend_class(Base, name="B200Backend"):
             self._cg_scal = None
             self._il_bufs = {}
 
+        def __del__(self):
+            try:
+                for plan in self._plans.values():
+                    self._lib.fft_plan_destroy(plan)
+                self._plans.clear()
+            except Exception:
+                pass
+
         # ------------------------------------------------------------ plumbing
         @property
         def _stream(self):
-            return self._torch.cuda.current_stream(self._device).cuda_stream
+            """Current torch stream of this backend's device.  Every primitive fetches it first, so this is
+            also where the device is made current: the C layer resolves per-device state (workspaces, SM
+            count, plans' twiddles) through cudaGetDevice, and a second backend on another GPU or a user's
+            torch.cuda.set_device must not redirect this one's launches."""
+            cuda = self._torch.cuda
+            if cuda.current_device() != self._device.index:
+                cuda.set_device(self._device)
+            return cuda.current_stream(self._device).cuda_stream
 
         def _pinned(self, arr):
             return getattr(arr, '_b200_pinned', False)
@@ -349,12 +415,13 @@ def make_backend_class(Base, name="B200Backend"):
             return self.dndarray(self, pinned.shape, pinned.dtype, own=False,
                                  data=DevPtr(pinned.ctypes.data, keep=pinned), name='mapped')
 
-        def NUFFT(self, M, N, coord, width=3, n=128, oversamp=None, dtype=_C64, **kwargs):
-            """Backend.NUFFT (backend.py:393-450) unchanged; the returned product remembers its arguments so that
-            indigo_b200.fused.fuse_transform can swap the SENSE tree it ends up in for the fused node."""
-            from .fused import tag_nufft
-            op = super().NUFFT(M, N, coord, width=width, n=n, oversamp=oversamp, dtype=dtype, **kwargs)
-            return tag_nufft(op, N, coord, width, n, oversamp)
+        if hasattr(Base, 'NUFFT'):
+            def NUFFT(self, M, N, coord, width=3, n=128, oversamp=None, dtype=_C64, **kwargs):
+                """Backend.NUFFT (backend.py:393-450) unchanged; the returned product remembers its arguments so
+                that indigo_b200.fused.fuse_transform can swap the SENSE tree it ends up in for the fused node."""
+                from .fused import tag_nufft
+                op = super().NUFFT(M, N, coord, width=width, n=n, oversamp=oversamp, dtype=dtype, **kwargs)
+                return tag_nufft(op, N, coord, width, n, oversamp)
 
         def barrier(self):
             self._lib.stream_sync(self._stream)
@@ -484,8 +551,10 @@ def make_backend_class(Base, name="B200Backend"):
             m, k = (int(v) for v in shape)
             if offsets.dtype != np.int32:
                 raise ValueError("b200 cdiamm needs int32 offsets, got %s" % offsets.dtype)
+            # data is (diagonal length x noffsets), column-major: its own row count is the diagonal length
+            # scipy chose (not necessarily k) and its leading dimension the pitch between diagonals
             self._lib.cdiamm(self._stream, 1 if adjoint else 0, m, k, int(x.shape[1]), int(offsets.size),
-                             offsets.ptr, data.ptr, ar, ai, x.ptr, x.ld, br, bi, y.ptr, y.ld)
+                             offsets.ptr, data.ptr, int(data.shape[0]), data.ld, ar, ai, x.ptr, x.ld, br, bi, y.ptr, y.ld)
 
         def onemm(self, y, x, alpha=1, beta=0):
             (ar, ai), (br, bi) = _re_im(alpha), _re_im(beta)
@@ -497,7 +566,10 @@ def make_backend_class(Base, name="B200Backend"):
             for p, n in arr._columns():
                 self._lib.fmax(self._stream, 2 * n, float(val), p)
 
-        class dia_matrix(Base.dia_matrix):
+        class dia_matrix(object):
+            """Device DIA holder of Backend.dia_matrix (backend.py:599-633): `data` is scipy's dia.data
+            transposed, (diagonal length x noffsets) column-major, whatever length scipy chose."""
+
             def __init__(self, backend, A, name='mat'):
                 assert isinstance(A, spp.dia_matrix)
                 A = A.astype(np.complex64)
@@ -506,6 +578,15 @@ def make_backend_class(Base, name="B200Backend"):
                 self.offsets = backend.copy_array(np.ascontiguousarray(A.offsets, dtype=np.int32), name=name + ".offsets")
                 self.shape, self.dtype = A.shape, A.dtype
                 self._row_frac = self._col_frac = 1
+
+            nbytes = property(lambda self: self.offsets.nbytes + self.data.nbytes)
+            nnz = property(lambda self: self.data.size)
+
+            def forward(self, y, x, alpha=1, beta=0):
+                self._backend.cdiamm(y, self.shape, self.offsets, self.data, x, alpha=alpha, beta=beta, adjoint=False)
+
+            def adjoint(self, y, x, alpha=1, beta=0):
+                self._backend.cdiamm(y, self.shape, self.offsets, self.data, x, alpha=alpha, beta=beta, adjoint=True)
 
         # ------------------------------------------------------------ solvers
         def pdot(self, x, y, comm):
@@ -528,6 +609,12 @@ def make_backend_class(Base, name="B200Backend"):
             operator, `team.allreduce_array` sums the partial A*p over ranks (NCCL) and
             the replicated vectors make every rank's scalars bit-identical, so no scalar
             all-reduce is needed."""
+            sums_image = team is not None and hasattr(team, 'allreduce_array')
+            replicated = team is None or bool(getattr(team, 'replicated_vectors', False))
+            if team is not None and not (sums_image and replicated):
+                # a reference-style team (only `allreduce(scalar)`) or partial vectors: every scalar has to go
+                # through pdot / pnorm2 exactly as backend.py:661-677 does, on the host
+                return self._cg_host_scalars(A, b_h, x_h, lamda, tol, maxiter, team, iterates)
             lib, s = self._lib, self._stream
             x, b = self.copy_array(x_h, name='x'), self.copy_array(b_h, name='b')
             n = int(x.size)
@@ -536,7 +623,7 @@ def make_backend_class(Base, name="B200Backend"):
 
             def apply(out, inp):
                 A.eval(out, inp)
-                if team is not None and hasattr(team, 'allreduce_array'):
+                if sums_image:
                     team.allreduce_array(out)
 
             apply(Ap, x)
@@ -570,9 +657,48 @@ def make_backend_class(Base, name="B200Backend"):
                 log.info("cg reached maxiter")
             x.copy_to(x_h)
 
+        def _cg_host_scalars(self, A, b_h, x_h, lamda, tol, maxiter, team, iterates=None):
+            """CG with the scalar protocol of the reference (backend.py:639-689): ||r||^2 and p^H A p are host
+            floats obtained through pnorm2 / pdot, which sum them over `team` unless its vectors are replicated.
+            Used whenever the device-resident-scalar loop of cg() cannot honour the team's contract."""
+            x, r = self.copy_array(x_h, name='x'), self.copy_array(b_h, name='b')
+            Ap = x.copy()
+            sums_image = hasattr(team, 'allreduce_array') and bool(getattr(team, 'replicated_vectors', False))
+
+            def apply(out, inp):
+                A.eval(out, inp)
+                if sums_image:
+                    team.allreduce_array(out)
+
+            apply(Ap, x)
+            self.axpby(1, r, -1, Ap)
+            self.axpby(1, r, -lamda, x)
+            p = r.copy(name='p')
+            rr = r0 = self.pnorm2(r, team)
+            for it in range(maxiter):
+                apply(Ap, p)
+                self.axpby(1, Ap, lamda, p)
+                step = rr / self.pdot(p, Ap, team)
+                self.axpby(1, x, step, p)
+                self.axpby(1, r, -step, Ap)
+                rr_new = self.pnorm2(r, team)
+                self.scale(p, rr_new / rr)
+                self.axpby(1, p, 1, r)
+                rr = rr_new
+                if iterates is not None:
+                    iterates.append(x.to_host())
+                resid = np.sqrt(rr / r0) if r0 else 0.0
+                log.info("iter %d, residual %g", it, resid)
+                if resid < tol:
+                    log.info("cg reached tolerance")
+                    break
+            else:
+                log.info("cg reached maxiter")
+            x.copy_to(x_h)
+
     B200Backend.__name__ = name
     B200Backend.__qualname__ = name
     return B200Backend
 
 
-B200Backend = make_backend_class(HostBackend)
+B200Backend = make_backend_class(StandaloneBase)

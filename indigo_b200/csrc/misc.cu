@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) onemm_kernel(int64_t m, int64_t k, c64 al
 
 // one thread per output element; blockIdx.y = right-hand-side column
 template <bool ADJ>
-__global__ void __launch_bounds__(256) diamm_kernel(int64_t yrows, int64_t xrows, int64_t dcols, int noff,
+__global__ void __launch_bounds__(256) diamm_kernel(int64_t yrows, int64_t xrows, int64_t dcols, int64_t dpitch, int noff,
                                                     const int32_t *__restrict__ offsets, const c64 *__restrict__ data,
                                                     c64 alpha, const c64 *__restrict__ X, int64_t ldx, c64 beta,
                                                     int beta_zero, c64 *__restrict__ Y, int64_t ldy) {
@@ -50,10 +50,10 @@ __global__ void __launch_bounds__(256) diamm_kernel(int64_t yrows, int64_t xrows
         const int64_t off = __ldg(offsets + d);
         if (!ADJ) {
             const int64_t j = r + off;                  // column of A; data is indexed by column
-            if (j >= 0 && j < xrows) acc = cfma(__ldg(data + j + (int64_t)d * dcols), __ldg(x + j), acc);
+            if (j >= 0 && j < xrows && j < dcols) acc = cfma(__ldg(data + j + (int64_t)d * dpitch), __ldg(x + j), acc);
         } else {
             const int64_t i = r - off;                  // row of A; r is the column
-            if (i >= 0 && i < xrows) acc = cfmac(__ldg(data + r + (int64_t)d * dcols), __ldg(x + i), acc);
+            if (i >= 0 && i < xrows && r < dcols) acc = cfmac(__ldg(data + r + (int64_t)d * dpitch), __ldg(x + i), acc);
         }
     }
     c64 out = cmul(alpha, acc);
@@ -85,9 +85,10 @@ int ib200_onemm(void *stream, int64_t m, int64_t ncols, int64_t k, float ar, flo
 }
 
 int ib200_cdiamm(void *stream, int adjoint, int64_t m, int64_t k, int64_t ncols, int64_t noffsets,
-                 const int32_t *offsets, const void *data, float ar, float ai, const void *X, int64_t ldx,
-                 float br, float bi, void *Y, int64_t ldy) {
+                 const int32_t *offsets, const void *data, int64_t data_cols, int64_t data_pitch, float ar, float ai,
+                 const void *X, int64_t ldx, float br, float bi, void *Y, int64_t ldy) {
     IB200_REQUIRE(m >= 0 && k >= 0 && ncols >= 0 && noffsets >= 0, "negative dimension");
+    IB200_REQUIRE(data_cols >= 0 && data_pitch >= data_cols, "diagonal pitch smaller than the diagonal length");
     const int64_t yrows = adjoint ? k : m, xrows = adjoint ? m : k;
     if (yrows == 0 || ncols == 0) return 0;
     IB200_REQUIRE(Y && X && (noffsets == 0 || (offsets && data)), "null pointer");
@@ -95,10 +96,10 @@ int ib200_cdiamm(void *stream, int adjoint, int64_t m, int64_t k, int64_t ncols,
     const dim3 grid((unsigned)ceil_div(yrows, 256), (unsigned)ncols);
     const int b0 = (br == 0.f && bi == 0.f) ? 1 : 0;
     if (adjoint)
-        diamm_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(yrows, xrows, k, (int)noffsets, offsets, (const c64 *)data,
+        diamm_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(yrows, xrows, data_cols, data_pitch, (int)noffsets, offsets, (const c64 *)data,
                                                                mk(ar, ai), (const c64 *)X, ldx, mk(br, bi), b0, (c64 *)Y, ldy);
     else
-        diamm_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(yrows, xrows, k, (int)noffsets, offsets, (const c64 *)data,
+        diamm_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(yrows, xrows, data_cols, data_pitch, (int)noffsets, offsets, (const c64 *)data,
                                                                 mk(ar, ai), (const c64 *)X, ldx, mk(br, bi), b0, (c64 *)Y, ldy);
     IB200_LAUNCH_CHECK();
     return 0;

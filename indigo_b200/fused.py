@@ -18,8 +18,9 @@ arithmetic runs as
 (fallbacks on stored entries: ib200_ccsrmm_ilr / ib200_ccsrmm_il; every stage has a switch on SenseDevice)
 so the 9.2 GB zero-padded volume of cfg3 is never written by a scatter, read back by the FFT,
 or transposed between the coil-slow layout of the interface and the coil-fast layout the
-gather wants.  The node below is an ordinary operator of the tree family the backend uses
-(`B.ops.Operator`): `A * x`, `A.H * y`, `(A.H * A) * x`, `B.cg(A.H * A, ...)` work as for the
+gather wants.  The node below is an ordinary operator of the family the backend uses (the reference's
+`indigo.operators.Operator` when the backend was built on the reference, indigo_b200.linop.Operator
+otherwise): `A * x`, `A.H * y`, `(A.H * A) * x`, `B.cg(A.H * A, ...)` work as for the
 unfused tree, and tests/test_gpu_fused.py checks all of them against the same oracle.
 """
 import ctypes
@@ -57,12 +58,15 @@ class SenseDevice(object):
             self.sample_tile = (int(os.environ["IB200_SAMPLE_TILE"]),) * 3
         if os.environ.get("IB200_RUN_LONG"):                        # tuning knob (tools/): run-length threshold
             self.run_long_thresh = int(os.environ["IB200_RUN_LONG"])
-        from .host.noncart import rolloff3
+        from .kbmath import rolloff3
 
         self.B = B
         lib, s = B._lib, B._stream
         N = tuple(int(v) for v in N)
         C = int(maps.shape[3])
+        if C > 32:
+            raise RuntimeError("fused SENSE path serves at most 32 coils per operator; shard or split the coils")
+        self._plan = None
         self.G, oN, omin, beta = gridding_matrix_device(B, N, coord, oversamp, weights, width, n)
         self.N, self.oN, self.C = N, tuple(int(v) for v in oN), C
         self.M = int(self.G.shape[0])
@@ -195,12 +199,10 @@ class SenseDevice(object):
         # multiplies its zero-weight taps (6th tap of on-grid samples) with whatever is there
         self.grid = B.zero_array((self.on * C,), _C64, name='grid[z][y][x][c]')
         self.ksp = B.empty_array((self.M * C,), _C64, name='ksp[m][c]')
-        if C > 32:
-            raise RuntimeError("fused SENSE path serves at most 32 coils per operator; shard or split the coils")
 
     def __del__(self):
         try:
-            if self._plan:
+            if getattr(self, '_plan', None):
                 self.B._lib.sense_plan_destroy(self._plan)
         except Exception:
             pass
@@ -246,7 +248,7 @@ class SenseDevice(object):
 
 
 def make_fused_classes(ops):
-    """Fused node classes on top of the operator family `ops` (indigo_b200.host.optree or the
+    """Fused node classes on top of the operator family `ops` (indigo_b200.linop or the
     reference's indigo.operators)."""
 
     class FusedSenseNUFFT(ops.Operator):
@@ -321,9 +323,8 @@ def sense_operator_fused(B, N, coord, maps, oversamp=2.0, weights=None, width=3,
     """The SENSE operator of examples/pics.py:92-95 as one fused node (same arguments as
     indigo_b200.sense.sense_operator).  Raises RuntimeError when the oversampled grid has no
     specialised FFT passes; callers then fall back to sense_operator_device / sense_operator."""
-    ops = B.ops if getattr(B, 'ops', None) is not None else None
-    if ops is None:
-        import indigo.operators as ops
+    from .sense import _ops_of
+    ops = _ops_of(B)
     if ops not in _cache:
         _cache[ops] = make_fused_classes(ops)
     Fwd, _ = _cache[ops]
@@ -400,11 +401,10 @@ def fuse_transform(B):
     """Transform class of B's operator family whose visit() swaps recognised SENSE trees for the fused node:
         A = A.optimize([fuse_transform(B)])        # or: sense_operator(B, ..., recipe=[fuse_transform(B)])
     Grids without specialised passes (RuntimeError from the plan) keep their tree."""
-    ops = getattr(B, 'ops', None)
-    if ops is not None and ops.__name__.startswith('indigo_b200'):
-        from .host.rewrites import Transform
-    else:
-        from indigo.transforms import Transform
+    if getattr(B, 'ops', None) is not None:
+        raise RuntimeError("fuse_transform rewrites trees of the reference's operator family; this backend was "
+                           "built without the reference package (use sense_operator_fused directly)")
+    from indigo.transforms import Transform
 
     class FuseSenseNUFFT(Transform):
         build = staticmethod(lambda backend, **kw: sense_operator_fused(backend, kw['N'], kw['coord'], kw['maps'], kw['oversamp'],

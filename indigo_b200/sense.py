@@ -15,16 +15,30 @@ import numpy as np
 _C64 = np.dtype('complex64')
 
 
+def _ops_of(B):
+    """Operator module of B's family: indigo_b200.linop for the standalone build, the reference's
+    indigo.operators when B was built on the reference's Backend (indigo_b200.register())."""
+    ops = getattr(B, 'ops', None)
+    if ops is None:
+        import indigo.operators as ops
+    return ops
+
+
 def sense_operator(B, N, coord, maps, oversamp=2.0, level=3, weights=None, recipe=None, width=3, n=128):
-    """Returns the optimised forward operator A (image -> multi-coil k-space).
+    """Returns the optimised forward operator A (image -> multi-coil k-space), built by the
+    REFERENCE's own builders and rewritten by its Transform machinery: B must be a backend
+    built on `indigo.backends.backend.Backend` (indigo_b200.register() / make_backend_class).
 
     N      image shape (N0, N1, N2)
     coord  (3, nread, nspokes...) sample positions in cycles/FOV, [-1/2, 1/2)
     maps   (N0, N1, N2, C) coil sensitivities
     weights optional per-sample row weights (sqrt density compensation), applied as
             Diag(w) * NUFFT like test_compat.py:185
-    recipe list of Transform classes; default = the reference's -O`level` recipe
-           taken from the same module family as B's operators."""
+    recipe list of Transform classes; default = the -O`level` recipe of examples/pics.py."""
+    if not hasattr(B, 'NUFFT'):
+        raise RuntimeError("sense_operator builds the reference's operator tree and needs a backend created by "
+                           "indigo_b200.register(); without the reference package use sense_operator_fused() "
+                           "or sense_operator_device()")
     coord = np.asarray(coord)
     Mshape = (1,) + tuple(coord.shape[1:])           # BART layout: READ dim of k-space is 1 (pics.py:60-63)
     F1 = B.NUFFT(Mshape, tuple(N), coord, width=width, n=n, oversamp=oversamp, dtype=_C64)
@@ -41,11 +55,7 @@ def sense_operator(B, N, coord, maps, oversamp=2.0, level=3, weights=None, recip
 
 
 def default_recipe(B, level=3):
-    """The -O`level` recipe built from the Transform family matching B's operators."""
-    ops = getattr(B, 'ops', None)
-    if ops is not None and ops.__name__.startswith('indigo_b200'):
-        from .host.rewrites import sense_recipe
-        return sense_recipe(level)
+    """The -O`level` recipe (examples/pics.py:179-191) on the reference's Transform family."""
     from .refcompat import reference_sense_recipe
     return reference_sense_recipe(level)
 
@@ -57,14 +67,16 @@ def normal_operator(A):
         return A.normal
     AHA = A.H * A
     AHA._name = 'SENSE'
-    # The arena reserved by A.optimize() is sized for A alone (transforms.py:72-76); A^H A nests one
-    # more Product temporary (the k-space vector).  The reference gets away with it because its
-    # estimate also counts the matrices' bytes; size the arena for the tree that is evaluated.
+    # Reference trees only: the arena reserved by A.optimize() is sized for A alone
+    # (transforms.py:72-76); A^H A nests one more Product temporary (the k-space vector).  The
+    # reference gets away with it because its estimate also counts the matrices' bytes; size the
+    # arena for the tree that is evaluated.
     B = A._backend
-    need = int(AHA.memusage()) // _C64.itemsize
-    if getattr(B, '_scratch', None) is not None and B._scratch.size < need and B._scratch_pos == 0:
-        B._scratch = None
-        B._scratch = B.empty_array((need,), _C64)
+    if getattr(B, '_scratch', None) is not None and hasattr(AHA, 'memusage'):
+        need = int(AHA.memusage()) // _C64.itemsize
+        if B._scratch.size < need and B._scratch_pos == 0:
+            B._scratch = None
+            B._scratch = B.empty_array((need,), _C64)
     return AHA
 
 
@@ -106,9 +118,17 @@ def _fftc_mod(oN):
     return np.exp(1j * 2.0 * np.pi * ph).astype(_C64)
 
 
-class DeviceBuiltSpMatrix(object):
-    """Mixin for SpMatrix leaves whose device matrix is produced by CUDA kernels from
-    the problem description instead of being uploaded from a scipy matrix."""
+def _sample_weights(weights, m):
+    """Per-sample row weights in sample order.  Samples are ordered like coord.reshape((3, -1), order='F'),
+    and B.Diag flattens its argument in memory order ('A'); an (nread, nspokes) array is therefore taken in
+    column-major order, a 1-D array as it is."""
+    w = np.asarray(weights, dtype=np.float32)
+    if w.ndim > 1:
+        w = np.asfortranarray(w).flatten(order='A')
+    if w.size != m:
+        raise ValueError("expected %d row weights, got %d" % (m, w.size))
+    return np.ascontiguousarray(w)
+
 
 
 def gridding_matrix_device(B, N, coord, oversamp=2.0, weights=None, width=3, n=128):
@@ -143,7 +163,7 @@ def gridding_matrix_device(B, N, coord, oversamp=2.0, weights=None, width=3, n=1
     colscale_d = B.copy_array(_fftc_mod_times_scale(oN))
     w_d = None
     if weights is not None:
-        w_d = B.copy_array(np.ascontiguousarray(np.asarray(weights, dtype=np.float32).reshape(-1)))
+        w_d = B.copy_array(_sample_weights(weights, m))
     lib.kb_fill(s, m, coord_d.ptr, grid, float(width), table_d.ptr, int(table.size),
                 w_d.ptr if w_d is not None else None, colscale_d.ptr, g_ptr.ptr, g_ind.ptr, g_val.ptr)
     B.barrier()
@@ -188,7 +208,7 @@ def kb_records_device(B, oN, coord, beta, weights=None, width=3, n=128, perm=Non
     f_d = [B.copy_array(np.ascontiguousarray(f)) for f in fac]
     w_d = None
     if weights is not None:
-        w_d = B.copy_array(np.ascontiguousarray(np.asarray(weights, dtype=np.float32).reshape(-1)))
+        w_d = B.copy_array(_sample_weights(weights, m))
     nb = int(lib.kb_record_bytes())
     rec = B.empty_array((max(m, 1) * nb // 8,), np.dtype('int64'), name='G.records')
     flag = ctypes.c_int()
@@ -199,25 +219,63 @@ def kb_records_device(B, oN, coord, beta, weights=None, width=3, n=128, perm=Non
     return rec if flag.value == 0 else None
 
 
+class _SixCallSense(object):
+    """Mixin with the evaluation of the -O3 tree's six Backend calls on
+    device-built operands; combined with the Operator base of B's family by sense_operator_device."""
+
+    def _setup(self, Gd, Pd, oN, C, nvox):
+        self.G, self.P = Gd, Pd                          # device CSR holders (B.csr_matrix.from_device)
+        self.oN, self.C, self.nvox = tuple(oN), int(C), int(nvox)
+        self.M, self.on = int(Gd.shape[0]), int(Gd.shape[1])
+        self._t = None
+
+    shape = property(lambda self: (self.M * self.C, self.nvox))
+    dtype = property(lambda self: _C64)
+
+    def _mem_usage(self, ncols=1):
+        return 0
+
+    def _temps(self):
+        if self._t is None:
+            B = self._backend
+            self._t = (B.empty_array((self.on * self.C, 1), _C64, name='SENSE1.grid.a'),
+                       B.empty_array((self.on * self.C, 1), _C64, name='SENSE1.grid.b'))
+        return self._t
+
+    def _eval(self, y, x, alpha=1, beta=0, forward=True, left=True):
+        if not left:
+            raise NotImplementedError("Right-multiplication not implemented for the six-call SENSE operator.")
+        assert x.shape[1] == 1, "one image / one multi-coil data set at a time"
+        B, C = self._backend, self.C
+        a, b = self._temps()
+        a3, b3 = a.reshape(self.oN + (C,)), b.reshape(self.oN + (C,))
+        a2, b2 = a.reshape((self.on, C)), b.reshape((self.on, C))
+        if forward:
+            self.P.adjoint(a, x)                                          # ccsrmm(P^H, adjoint): expand
+            B.fftn(b3, a3)                                                # fftn
+            self.G.forward(y.reshape((self.M, C)), b2, alpha=alpha, beta=beta)    # ccsrmm(G')
+        else:
+            self.G.adjoint(a2, x.reshape((self.M, C)))                    # ccsrmm(G', adjoint)
+            B.ifftn(b3, a3)                                               # ifftn
+            self.P.forward(y, b, alpha=alpha, beta=beta)                  # ccsrmm(P^H): combine
+
+
 def sense_operator_device(B, N, coord, maps, oversamp=2.0, weights=None, width=3, n=128):
-    """Same operator, same -O3 tree shape and the same six backend calls per A^H A as
-    sense_operator(), but G' and P^H are built on the GPU (ib200_kb_* / ib200_sense_ph_*)
+    """Same operator and the same six Backend calls per A^H A as the -O3 tree of
+    sense_operator(), issued directly (no tree, works without the reference package); G' and P^H are built on the GPU (ib200_kb_* / ib200_sense_ph_*)
     straight into device CSR arrays: no COO triplets, no scipy products, no 10 GB upload.
     Needed at BASELINE.json's full sizes (416^3 grid, 6.8 M samples: 853 M stored entries).
     tests/test_gpu_sense.py checks structure (bit-identical) and values against the
     host-built matrices."""
     import ctypes
     from scipy.signal.windows import kaiser
-    from .host.noncart import rolloff3
-    from .host import optree as op
+    from .kbmath import rolloff3
 
     lib, s = B._lib, B._stream
     N = tuple(int(v) for v in N)
     C = int(maps.shape[3])
     Gd, oN, omin, beta = gridding_matrix_device(B, N, coord, oversamp, weights, width, n)
     on, nvox = int(np.prod(oN)), int(np.prod(N))
-    from .host.noncart import rolloff3
-    from .host import optree as op
 
     # ---- P^H, stored adjoint of kron(I_C, mod*zpad*apod) * vstack(maps) ----------------
     cut = tuple(slice(a // 2 + int(np.ceil(-b / 2)), a // 2 + int(np.ceil(b / 2))) for a, b in zip(oN, N))
@@ -242,27 +300,14 @@ def sense_operator_device(B, N, coord, maps, oversamp=2.0, weights=None, width=3
     Pd = B.csr_matrix.from_device(B, (nvox, C * on), p_ptr, p_ind[0:pnnz], p_val[0:pnnz],
                                   name='((x)mod*zpad*apod)*+.H')
 
-    # ---- the -O3 tree around them (shape of examples/pics.py -O3 output) -----
-    class _DevSp(op.SpMatrix, DeviceBuiltSpMatrix):
-        def __init__(self, backend, dev, name):
-            op.Operator.__init__(self, backend, name=name)
-            self._matrix, self._matrix_d = None, dev
-            self._allow_exwrite, self._use_dia = True, False
+    # ---- the six calls around them (what the -O3 tree of examples/pics.py evaluates) ----
+    ops = _ops_of(B)
+    cls = _six_cache.get(ops)
+    if cls is None:
+        cls = _six_cache[ops] = type('SixCallSense', (_SixCallSense, ops.Operator), {})
+    A = cls(B, name='SENSE1')
+    A._setup(Gd, Pd, oN, C, nvox)
+    return A
 
-        shape = property(lambda self: self._matrix_d.shape)
-        dtype = property(lambda self: _C64)
-        nnz = property(lambda self: int(self._matrix_d.nnz))
 
-        def _mem_usage(self, ncols=1):
-            return int(self._matrix_d.values.nbytes)
-
-        def _get_or_create_device_matrix(self):
-            return self._matrix_d
-
-    _DevSp.__name__ = 'SpMatrix'          # tree visitors dispatch on the class name
-    Gn = _DevSp(B, Gd, 'interp*mod*scale')
-    Pn = _DevSp(B, Pd, '((x)mod*zpad*apod)*+.H')
-    F = B.UnscaledFFT(oN, _C64, name='fft')
-    A = B.KronI(C, Gn) * (B.KronI(C, F) * Pn.H)
-    A._name = 'SENSE1'
-    return A.optimize([])
+_six_cache = {}

@@ -1,6 +1,6 @@
 """
 Host-side test of the fusion Transform (indigo_b200.fused.fuse_transform): the tree of
-examples/pics.py:92-95, built by the unchanged builders, is recognised, the arguments of the fused node are
+examples/pics.py:92-95, built by the REFERENCE's own builders on its NumpyBackend, is recognised, the arguments of the fused node are
 recovered bit-exactly from it (trajectory from the NUFFT tag, maps and row weights from the diagonal matrices),
 and any other tree is left alone.  The fused node itself needs a GPU (tests/test_gpu_fused.py); here its
 constructor is replaced by a recorder.
@@ -11,7 +11,7 @@ import scipy.sparse as spp
 from indigo_b200 import synth
 from indigo_b200.fused import fuse_transform, match_sense_tree, tag_nufft
 from indigo_b200.sense import sqrt_dcf
-from np_host_backend import NpHostBackend
+from refenv import numpy_backend as NpHostBackend
 
 C64 = np.dtype('complex64')
 

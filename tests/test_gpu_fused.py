@@ -210,12 +210,14 @@ def test_fused_refuses_unsupported_grid(B):
         sense_operator_fused(B, N, coord, maps, 2.0)
 
 
-def test_fuse_transform_swaps_the_pics_tree(B):
-    """The tree of examples/pics.py:92-95 built by the unchanged builders (B.NUFFT, B.KronI, B.VStack, B.Diag) and
+def test_fuse_transform_swaps_the_pics_tree():
+    """The tree of examples/pics.py:92-95 built by the reference's own builders (B.NUFFT, B.KronI, B.VStack, B.Diag) and
     handed to the fusion Transform comes back as the fused node and matches the oracle; a grid without
     specialised passes keeps its tree and still evaluates (six-call path)."""
     from indigo_b200.fused import fuse_transform
     from indigo_b200.sense import sense_operator
+    from refenv import b200_reference_backend
+    B = b200_reference_backend(0)
     N, C = (16, 16, 16), 4
     rs, coord, maps, w = _setup(N, C, "koosh", True)
     A = sense_operator(B, N, coord, maps, 2.0, weights=w, recipe=[fuse_transform(B)])

@@ -1,8 +1,11 @@
 """
-GPU parity tests of the north-star path: the -O3 SENSE-NUFFT tree evaluated by
-B200Backend against (a) golden vectors from the unmodified reference NumpyBackend
-and (b) the numpy oracle on the same seeded inputs.  Bar (BASELINE.json): CSR
-structure bit-identical; rel-L2 <= 1e-5 on A x, A^H y, A^H A x and CG iterates.
+GPU parity tests of the north-star path: the -O3 SENSE-NUFFT tree -- built by the REFERENCE's own
+builders (backend.py:287-448), rewritten by its own Transform machinery and walked by its own
+operators.py, on a B200Backend derived from the reference's Backend (tests/refenv.py) -- against
+(a) golden vectors from the unmodified reference NumpyBackend and (b) the numpy oracle on the same
+seeded inputs; then the same six calls issued directly by the standalone build
+(sense_operator_device).  Bar (BASELINE.json): CSR structure bit-identical; rel-L2 <= 1e-5 on
+A x, A^H y, A^H A x and CG iterates.
 """
 import hashlib
 import os
@@ -12,8 +15,8 @@ import pytest
 
 from indigo_b200 import synth
 from indigo_b200.sense import sense_operator, normal_operator, sqrt_dcf
-from indigo_b200.host import operators as op
 from oracle import sense as osense, np_oracle as K
+from refenv import b200_reference_backend
 
 pytestmark = pytest.mark.gpu
 C64 = np.dtype('complex64')
@@ -22,6 +25,13 @@ TOL = 1e-5
 
 @pytest.fixture(scope="module")
 def B():
+    """B200Backend on the reference's Backend base: trees are the reference's own."""
+    return b200_reference_backend(0)
+
+
+@pytest.fixture(scope="module")
+def SB():
+    """Standalone build (no reference package involved)."""
     from indigo_b200 import B200Backend
     return B200Backend(0)
 
@@ -36,10 +46,14 @@ def sha(a):
 
 
 def leaves(A):
+    """Device matrices (G', P^H) of the operator: SpMatrix leaves of a reference tree, or the operands of
+    the standalone six-call operator."""
+    if hasattr(A, 'G') and hasattr(A, 'P'):
+        return A.G, A.P
     found = []
 
     def walk(n):
-        if isinstance(n, op.SpMatrix):
+        if type(n).__name__ == 'SpMatrix':
             found.append(n)
         for c in getattr(n, '_children', []):
             walk(c)
@@ -82,7 +96,7 @@ def test_cg_iterates_against_reference_golden(B, golden_dir, name):
     for k, (mine, ref) in enumerate(zip(its, g["cg_iterates"])):
         assert relerr(mine, ref) < TOL, (k, relerr(mine, ref))
     assert relerr(x, g["cg_iterates"][-1]) < TOL
-    # the unfused reference update order (HostBackend.cg through the same kernels) agrees too
+    # the reference's own Backend.cg (backend.py:639-689, host scalars) through the same kernels agrees too
     x2 = np.zeros_like(g["cg_b"], order='F')
     super(type(B), B).cg(AHA, g["cg_b"], x2, lamda=float(g["cg_lamda"]), maxiter=len(g["cg_iterates"]), tol=0.0)
     assert relerr(x2, g["cg_iterates"][-1]) < TOL
@@ -166,7 +180,8 @@ def test_reduced_cfg3_against_oracle(B):
 
 
 @pytest.mark.parametrize("name", ["sense_small", "sense_odd"])
-def test_device_built_operator_matches_reference(B, golden_dir, name):
+def test_device_built_operator_matches_reference(SB, golden_dir, name):
+    B = SB
     """G' and P^H built by CUDA kernels from (coord, maps): CSR structure bit-identical to the
     reference's, values bit-identical (no aliasing taps in these grids), applies within 1e-5."""
     from indigo_b200.sense import sense_operator_device
@@ -189,7 +204,8 @@ def test_device_built_operator_matches_reference(B, golden_dir, name):
     assert relerr(x, g["cg_iterates"][-1]) < TOL
 
 
-def test_device_built_cfg1_structure(B, golden_dir):
+def test_device_built_cfg1_structure(SB, golden_dir):
+    B = SB
     """Config 1 has a 2-point z axis: 5-6 taps alias onto 2 cells and are merged."""
     from indigo_b200.sense import sense_operator_device
     g = np.load(os.path.join(golden_dir, "sense_cfg1_digest.npz"))
