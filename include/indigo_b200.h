@@ -297,6 +297,13 @@ int ib200_sense_plan_set_support(ib200_sense_plan plan, const int32_t *win, int 
 int ib200_sense_expand_fft(ib200_sense_plan plan, void *stream, void *grid_il, const void *img, const void *pf);
 int ib200_sense_ifft_combine(ib200_sense_plan plan, void *stream, void *img_out, void *grid_il, const void *pf,
                              float alpha_re, float alpha_im, float beta_re, float beta_im);
+/* One pass of the two fused transforms on its own -- the same kernels with the same arguments as inside
+ * ib200_sense_expand_fft / ib200_sense_ifft_combine -- so that a caller (bench.py) can bracket every
+ * kernel of UnscaledFFT's replacement (operators.py:311-338) with CUDA events:
+ *   which = 0 expand + x pass (img, pf -> grid), 1 forward y, 2 forward z,
+ *           3 inverse z, 4 inverse y, 5 x pass + coil combine (grid, pf -> img_out, alpha/beta as above). */
+int ib200_sense_pass(ib200_sense_plan plan, void *stream, int which, void *grid_il, const void *img,
+                     void *img_out, const void *pf, float alpha_re, float alpha_im, float beta_re, float beta_im);
 
 /* ------------------------------------------------------------------ operator construction on the device
  * Setup-time replacements for the host construction of the two sparse factors

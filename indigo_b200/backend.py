@@ -601,14 +601,18 @@ def make_backend_class(Base, name="B200Backend"):
                 v = comm.allreduce(v)
             return v
 
-        def cg(self, A, b_h, x_h, lamda=0.0, tol=1e-10, maxiter=100, team=None, iterates=None):
+        def cg(self, A, b_h, x_h, lamda=0.0, tol=1e-10, maxiter=100, team=None, iterates=None, graph=False):
             """Conjugate gradient on (A + lamda I) x = b with the update order of
             backend.py:639-689, but with the five BLAS-1 passes and two blocking scalar
             read-backs of one iteration fused into three kernels whose scalars stay on the
             device (ib200_cdotc_dev / ib200_cg_xr / ib200_cg_p).  With a coil-sharded
             operator, `team.allreduce_array` sums the partial A*p over ranks (NCCL) and
             the replicated vectors make every rank's scalars bit-identical, so no scalar
-            all-reduce is needed."""
+            all-reduce is needed.
+
+            graph=True (needs tol <= 0 and no `iterates`): one iteration -- the apply, the collective and the
+            three solver kernels -- is captured in a CUDA graph after a first eager iteration and replayed
+            maxiter - 1 times, one launch per iteration (the launch-bound regime, cfg1)."""
             sums_image = team is not None and hasattr(team, 'allreduce_array')
             replicated = team is None or bool(getattr(team, 'replicated_vectors', False))
             if team is not None and not (sums_image and replicated):
@@ -638,13 +642,33 @@ def make_backend_class(Base, name="B200Backend"):
             r0 = None
             if tol > 0:
                 r0 = float(scal[0].item())
-            for it in range(maxiter):
+
+            def iteration():
+                st = self._stream
                 apply(Ap, p)
                 if lamda != 0:
                     self.axpby(1, Ap, lamda, p)
-                lib.cdotc_dev(s, n, p.ptr, Ap.ptr, sp + 8)            # scal[1..2] = p^H Ap
-                lib.cg_xr(s, n, x.ptr, r.ptr, p.ptr, Ap.ptr, sp)      # x, r, scal[3] = ||r||^2
-                lib.cg_p(s, n, p.ptr, r.ptr, sp)                      # p, scal[0] = scal[3]
+                lib.cdotc_dev(st, n, p.ptr, Ap.ptr, sp + 8)           # scal[1..2] = p^H Ap
+                lib.cg_xr(st, n, x.ptr, r.ptr, p.ptr, Ap.ptr, sp)     # x, r, scal[3] = ||r||^2
+                lib.cg_p(st, n, p.ptr, r.ptr, sp)                     # p, scal[0] = scal[3]
+
+            if graph and tol <= 0 and iterates is None and maxiter > 2:
+                torch = self._torch
+                iteration()                                            # eager: first-use allocations and attributes
+                side = torch.cuda.Stream(device=self._device)
+                side.wait_stream(torch.cuda.current_stream(self._device))
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.stream(side):
+                    with torch.cuda.graph(g, stream=side):
+                        iteration()
+                torch.cuda.current_stream(self._device).wait_stream(side)
+                for it in range(maxiter - 1):                          # capturing records the iteration, it does not run it
+                    g.replay()
+                log.info("cg reached maxiter (graph replay)")
+                x.copy_to(x_h)
+                return
+            for it in range(maxiter):
+                iteration()
                 if iterates is not None:
                     iterates.append(x.to_host())
                 if tol > 0:

@@ -249,6 +249,7 @@ using namespace ib200;
 extern "C" {
 
 int ib200_caxpby(void *stream, int64_t n, float br, float bi, void *y, float ar, float ai, const void *x) {
+    IB200_RANGE("ib200_caxpby");
     IB200_REQUIRE(n >= 0, "negative length");
     if (n == 0) return 0;
     IB200_REQUIRE(y != nullptr, "null y");
@@ -272,6 +273,7 @@ int ib200_cscal(void *stream, int64_t n, float ar, float ai, void *x) {
 }
 
 int ib200_cdotc_dev(void *stream, int64_t n, const void *x, const void *y, double *dev_out2) {
+    IB200_RANGE("ib200_cdotc_dev");
     IB200_REQUIRE(n >= 0 && dev_out2, "bad arguments");
     ReduceWs *w; int rc = get_ws(&w); if (rc) return rc;
     const int slot = next_slot(w);
@@ -315,6 +317,7 @@ int ib200_scnrm2sq(void *stream, int64_t n, const void *x, double *host_out) {
 }
 
 int ib200_cg_xr(void *stream, int64_t n, void *x, void *r, const void *p, const void *Ap, double *scal) {
+    IB200_RANGE("ib200_cg_xr");
     IB200_REQUIRE(n >= 0 && x && r && p && Ap && scal, "bad arguments");
     ReduceWs *w; int rc = get_ws(&w); if (rc) return rc;
     const int slot = next_slot(w);
@@ -326,6 +329,7 @@ int ib200_cg_xr(void *stream, int64_t n, void *x, void *r, const void *p, const 
 }
 
 int ib200_cg_p(void *stream, int64_t n, void *p, const void *r, double *scal) {
+    IB200_RANGE("ib200_cg_p");
     IB200_REQUIRE(n >= 0 && p && r && scal, "bad arguments");
     ReduceWs *w; int rc = get_ws(&w); if (rc) return rc;
     const int slot = next_slot(w);

@@ -5,6 +5,8 @@
 #include <cstdint>
 #include <cstdio>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/indigo_b200.h"
 
 namespace ib200 {
@@ -39,9 +41,20 @@ void count_launch(int n = 1);
         IB200_TRY(cudaGetLastError());                                               \
     } while (0)
 
+// NVTX range around a C-ABI call (ranges per backend call / fused step, visible in
+// Nsight Systems and in ncu's --nvtx filters; header-only NVTX3, a no-op without an attached tool)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+#define IB200_RANGE(name) ::ib200::NvtxRange _ib200_range(name)
+
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int sm_count();             // SMs of the current device (cached)
+// fork a per-device side stream off `main` / join it back (core.cu); every begin must be followed by an end
+int side_stream_begin(cudaStream_t main, cudaStream_t *side);
+int side_stream_end(cudaStream_t main);
 int64_t smem_optin();       // max opt-in dynamic shared memory per block
 
 // ---- complex64 arithmetic on float2 ----------------------------------------

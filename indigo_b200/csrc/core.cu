@@ -33,6 +33,38 @@ static void refresh_dev() {
     g_dev.dev = dev; g_dev.sms = sms; g_dev.smem = smem;
 }
 
+// Side stream per device (streams and events are created once per device and kept for the life of the
+// process): small latency-bound kernels that are independent of a call's main kernel are forked onto it
+// and joined back with events, so that both share the SMs instead of running back to back.  The
+// fork/join pattern is capturable in a CUDA graph.
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static SideStream g_side[64];
+
+int side_stream_begin(cudaStream_t main, cudaStream_t *side) {
+    int dev = 0;
+    IB200_TRY(cudaGetDevice(&dev));
+    SideStream &q = g_side[dev & 63];
+    if (!q.s) {
+        IB200_TRY(cudaStreamCreateWithFlags(&q.s, cudaStreamNonBlocking));
+        IB200_TRY(cudaEventCreateWithFlags(&q.fork, cudaEventDisableTiming));
+        IB200_TRY(cudaEventCreateWithFlags(&q.join, cudaEventDisableTiming));
+    }
+    IB200_TRY(cudaEventRecord(q.fork, main));
+    IB200_TRY(cudaStreamWaitEvent(q.s, q.fork, 0));
+    *side = q.s;
+    return 0;
+}
+
+int side_stream_end(cudaStream_t main) {
+    int dev = 0;
+    IB200_TRY(cudaGetDevice(&dev));
+    SideStream &q = g_side[dev & 63];
+    IB200_REQUIRE(q.s != nullptr, "side stream was never opened on this device");
+    IB200_TRY(cudaEventRecord(q.join, q.s));
+    IB200_TRY(cudaStreamWaitEvent(main, q.join, 0));
+    return 0;
+}
+
 int sm_count() { refresh_dev(); return g_dev.sms > 0 ? g_dev.sms : 148; }
 int64_t smem_optin() { refresh_dev(); return g_dev.smem > 0 ? g_dev.smem : 232448; }
 

@@ -418,6 +418,7 @@ int ib200_ccsrmm(void *stream, int adjoint, int exwrite, int64_t m, int64_t k, i
                  float ar, float ai,
                  const void *vals, const int32_t *colind, const int32_t *rowptr, const void *X, int64_t ldx,
                  float br, float bi, void *Y, int64_t ldy) {
+    IB200_RANGE("ib200_ccsrmm");
     IB200_REQUIRE(m >= 0 && k >= 0 && ncols >= 0 && nnz >= 0, "negative dimension");
     IB200_REQUIRE(m < (1LL << 31) && k < (1LL << 31) && nnz < (1LL << 31), "int32 CSR indices: dimensions must be < 2^31");
     const int64_t yrows = adjoint ? k : m, xrows = adjoint ? m : k;

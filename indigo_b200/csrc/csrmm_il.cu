@@ -346,36 +346,8 @@ __global__ void __launch_bounds__(256) long_rows_kernel(int64_t m, const int32_t
 }
 
 // The long-row kernel is latency bound (one CTA per row, few CTAs) and independent of the main
-// gather: it runs on a side stream, forked from and joined back into the caller's stream with
-// events, so that both kernels share the SMs instead of running back to back.
-struct SideStream {
-    cudaStream_t s = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
-    int dev = -1;
-};
-static thread_local SideStream g_side;
-
-static int side_stream_begin(cudaStream_t main, cudaStream_t *side) {
-    int dev = 0;
-    IB200_TRY(cudaGetDevice(&dev));
-    if (g_side.dev != dev) {
-        IB200_TRY(cudaStreamCreateWithFlags(&g_side.s, cudaStreamNonBlocking));
-        IB200_TRY(cudaEventCreateWithFlags(&g_side.fork, cudaEventDisableTiming));
-        IB200_TRY(cudaEventCreateWithFlags(&g_side.join, cudaEventDisableTiming));
-        g_side.dev = dev;
-    }
-    IB200_TRY(cudaEventRecord(g_side.fork, main));
-    IB200_TRY(cudaStreamWaitEvent(g_side.s, g_side.fork, 0));
-    *side = g_side.s;
-    return 0;
-}
-
-static int side_stream_end(cudaStream_t main) {
-    IB200_TRY(cudaEventRecord(g_side.join, g_side.s));
-    IB200_TRY(cudaStreamWaitEvent(main, g_side.join, 0));
-    return 0;
-}
-
+// gather: it runs on the device's side stream (core.cu), forked from and joined back into the caller's
+// stream with events, so that both kernels share the SMs instead of running back to back.
 template <bool PACKED>
 static int launch_long(cudaStream_t s, int CL, int nlong, const int32_t *longrows, int C, c64 alpha, const void *ent,
                        const c64 *vals, const int32_t *colind, const int32_t *rowptr, const c64 *Xil, int64_t xpitch,
@@ -663,6 +635,7 @@ static int interleave_impl(void *stream, int64_t rows, int64_t ncols, const void
 }
 
 int ib200_interleave(void *stream, int64_t rows, int64_t ncols, const void *X, int64_t ldx, void *Xil, int64_t pitch) {
+    IB200_RANGE("ib200_interleave");
     return interleave_impl(stream, rows, ncols, X, ldx, Xil, pitch, nullptr);
 }
 
@@ -692,6 +665,7 @@ static int deinterleave_impl(void *stream, int64_t rows, int64_t ncols, const vo
 
 int ib200_deinterleave(void *stream, int64_t rows, int64_t ncols, const void *Yil, int64_t pitch, float br, float bi,
                        void *Y, int64_t ldy) {
+    IB200_RANGE("ib200_deinterleave");
     return deinterleave_impl(stream, rows, ncols, Yil, pitch, br, bi, Y, ldy, nullptr);
 }
 
@@ -713,6 +687,7 @@ int ib200_ccsrmm_il(void *stream, int64_t m, int64_t k, int64_t ncols, int64_t n
                     const void *vals, const int32_t *colind, const int32_t *rowptr, const void *Xil, int64_t xpitch,
                     void *Yil, int64_t ypitch, const int32_t *rowmap, int rows_per_group,
                     const int32_t *longrows, int nlong, int long_thresh) {
+    IB200_RANGE("ib200_ccsrmm_il");
     IB200_REQUIRE(m >= 0 && k >= 0 && ncols >= 0 && nnz >= 0, "negative dimension");
     IB200_REQUIRE(m < (1LL << 31) && k < (1LL << 31) && nnz < (1LL << 31), "int32 CSR indices: dimensions must be < 2^31");
     IB200_REQUIRE(ncols <= 32, "interleaved SpMM serves at most 32 columns per call");
@@ -840,6 +815,7 @@ int ib200_ccsrmm_ilr(void *stream, int64_t m, int64_t k, int64_t ncols, int64_t 
                      const void *packed, const int32_t *rowptr, const void *Xil, int64_t xpitch,
                      void *Yil, int64_t ypitch, const int32_t *rowmap, int rows_per_group,
                      const int32_t *longrows, int nlong, int long_thresh) {
+    IB200_RANGE("ib200_ccsrmm_ilr");
     IB200_REQUIRE(m >= 0 && k >= 0 && ncols >= 0 && nnz >= 0, "negative dimension");
     IB200_REQUIRE(m < (1LL << 31) && k < (1LL << 31) && nnz < (1LL << 31), "int32 CSR indices: dimensions must be < 2^31");
     IB200_REQUIRE(ncols <= 32, "interleaved SpMM serves at most 32 columns per call");
@@ -863,7 +839,7 @@ int ib200_ccsrmm_ilr(void *stream, int64_t m, int64_t k, int64_t ncols, int64_t 
         if (rc) return rc;
         rc = launch_long<true>(side, CL, nlong, longrows, (int)ncols, alpha, packed, nullptr, nullptr, rowptr,
                                (const c64 *)Xil, xpitch, (c64 *)Yil, ypitch, rowmap);
-        if (rc) return rc;
+        if (rc) { side_stream_end(s); return rc; }
         rc = ilr_main(s, staged, CL, avg, rows_per_group, m, ncols, alpha, packed, rowptr, Xil, xpitch, Yil, ypitch, rowmap,
                       long_thresh);
         const int rc2 = side_stream_end(s);

@@ -19,6 +19,7 @@
 // run in segment order, so the result does not depend on scheduling.
 #include "common.cuh"
 #include "pk2.cuh"
+#include <cstdlib>
 
 namespace ib200 {
 
@@ -364,6 +365,7 @@ int ib200_ccsrmm_runs(void *stream, int64_t kp, int64_t ncols, float ar, float a
                       const int32_t *ids, const void *w4, const void *Xil, int64_t xpitch, void *Yil, int64_t ypitch,
                       const int32_t *rowmap, int seg_len, const int32_t *seg_desc, int nseg, const int32_t *split_desc,
                       int nsplit, void *scratch) {
+    IB200_RANGE("ib200_ccsrmm_runs");
     IB200_REQUIRE(kp >= 0 && kp % kRun == 0 && kp < (1LL << 31), "row count must be a multiple of 4");
     if (kp == 0 || ncols == 0) return 0;
     IB200_REQUIRE(ncols > 0 && ncols <= 64 && ncols % 2 == 0, "run gather serves an even number of at most 64 columns");
@@ -377,7 +379,11 @@ int ib200_ccsrmm_runs(void *stream, int64_t kp, int64_t ncols, float ar, float a
     const c64 alpha = mk(ar, ai);
     cudaStream_t s = as_stream(stream);
     const int CL = runs_pow2_ceil(ncols / 2);
-    const int PL = CL >= 4 ? 1 : kRun / CL;                         // lanes of a group split the run's points when coils are few
+    int PL = CL >= 4 ? 1 : kRun / CL;                               // lanes of a group split the run's points when coils are few
+    if (const char *e = getenv("IB200_RUNS_PL")) {                   // tuning knob (tools/): points-split factor 1, 2 or 4
+        const int v = atoi(e);
+        if ((v == 1 || v == 2 || v == 4) && CL * v <= 32 && (CL < 4 || v == 1)) PL = v;
+    }
     const int rpg = 4;
     const int GPB = 256 / (CL * PL);
     const int64_t blocks = ceil_div(nruns, (int64_t)GPB * rpg);
@@ -392,13 +398,17 @@ int ib200_ccsrmm_runs(void *stream, int64_t kp, int64_t ncols, float ar, float a
             IB200_TRY(cudaFuncSetAttribute(csrmm_runs_seg_kernel<cl, pl>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes)); \
         }                                                                                                              \
         if (nseg > 0) {                                                                                                \
-            csrmm_runs_seg_kernel<cl, pl><<<(unsigned)ceil_div(nseg, GPB), 256, ring_bytes, s>>>(nseg, (int)ncols, (const int4 *)seg_desc, ids, \
+            /* few, long, latency-bound lane groups: on the side stream, sharing the SMs with the main kernel */      \
+            rc = side_stream_begin(s, &side);                                                                          \
+            if (rc) return rc;                                                                                         \
+            csrmm_runs_seg_kernel<cl, pl><<<(unsigned)ceil_div(nseg, GPB), 256, ring_bytes, side>>>(nseg, (int)ncols, (const int4 *)seg_desc, ids, \
                                                                                    (const float4 *)w4, (const c64 *)Xil, pb,  \
                                                                                    (c64 *)scratch, cpitch);           \
             count_launch();                                                                                            \
         }                                                                                                              \
         csrmm_runs_kernel<cl, pl><<<(unsigned)blocks, 256, ring_bytes, s>>>(nruns, (int)ncols, alpha, run_ptr, ids, (const float4 *)w4, \
                                                                (const c64 *)Xil, pb, (c64 *)Yil, ypitch, rowmap, seg_len, rpg); \
+        if (nseg > 0) { rc = side_stream_end(s); if (rc) return rc; }                                                  \
         if (nsplit > 0) {                                                                                              \
             count_launch();                                                                                            \
             csrmm_runs_fold_kernel<cl, pl><<<(unsigned)ceil_div(nsplit, GPB), 256, 0, s>>>(nsplit, (int)ncols, alpha,  \
@@ -406,8 +416,11 @@ int ib200_ccsrmm_runs(void *stream, int64_t kp, int64_t ncols, float ar, float a
                                                                                       cpitch, (c64 *)Yil, ypitch, rowmap); \
         }                                                                                                              \
         break
+    int rc = 0;
+    cudaStream_t side = nullptr;
     switch (CL * 8 + PL) {
-        IB200_RUNS_CASE(1, 4); IB200_RUNS_CASE(2, 2); IB200_RUNS_CASE(4, 1); IB200_RUNS_CASE(8, 1); IB200_RUNS_CASE(16, 1);
+        IB200_RUNS_CASE(1, 4); IB200_RUNS_CASE(1, 2); IB200_RUNS_CASE(1, 1); IB200_RUNS_CASE(2, 2); IB200_RUNS_CASE(2, 1);
+        IB200_RUNS_CASE(4, 1); IB200_RUNS_CASE(8, 1); IB200_RUNS_CASE(16, 1);
         IB200_RUNS_CASE(32, 1);
         default: set_error("internal: no run gather for CL=%d PL=%d", CL, PL); return IB200_E_UNSUPPORTED;
     }

@@ -419,6 +419,7 @@ int ib200_fft_plan_describe(ib200_fft_plan plan, int axis, int *radices, int max
 }
 
 int ib200_fft_exec(ib200_fft_plan plan, void *stream, void *y, const void *x, int direction) {
+    IB200_RANGE("ib200_fft_exec");
     IB200_REQUIRE(plan, "null plan");
     return exec_impl(&plan->d, as_stream(stream), (c64 *)y, (const c64 *)x, direction, nullptr, 0, nullptr, 0);
 }
@@ -504,6 +505,7 @@ int ib200_sense_plan_create(ib200_sense_plan *plan, const int64_t N[3], const in
     IB200_REQUIRE(plan && N && oN, "null pointer");
     IB200_REQUIRE(ncoils >= 1, "need at least one coil");
     for (int d = 0; d < 3; ++d) IB200_REQUIRE(N[d] >= 1 && oN[d] >= N[d], "grid must be at least as large as the image");
+    IB200_REQUIRE(oN[0] * ncoils >= kSpecL, "grid row too short");
     ib200_sense_plan_s *p = new (std::nothrow) ib200_sense_plan_s();
     if (!p) { set_error("out of host memory"); return IB200_E_NOMEM; }
     int rc = ib200_fft_plan_create(&p->fft, 3, oN, ncoils);
@@ -522,7 +524,6 @@ int ib200_sense_plan_create(ib200_sense_plan *plan, const int64_t N[3], const in
             return IB200_E_UNSUPPORTED;
         }
     }
-    IB200_REQUIRE(oN[0] * ncoils >= kSpecL, "grid row too short");
     p->C = ncoils;
     *plan = p;
     return 0;
@@ -562,6 +563,7 @@ static void sense_args(ib200_sense_plan_s *p, SenseFftArgs *a) {
 }
 
 int ib200_sense_expand_fft(ib200_sense_plan plan, void *stream, void *grid_il, const void *img, const void *pf) {
+    IB200_RANGE("ib200_sense_expand_fft");
     IB200_REQUIRE(plan && grid_il && img && pf, "null pointer");
     int rc = ensure_device_state(&plan->fft->d);
     if (rc) return rc;
@@ -578,6 +580,7 @@ int ib200_sense_expand_fft(ib200_sense_plan plan, void *stream, void *grid_il, c
 
 int ib200_sense_ifft_combine(ib200_sense_plan plan, void *stream, void *img_out, void *grid_il, const void *pf,
                              float ar, float ai, float br, float bi) {
+    IB200_RANGE("ib200_sense_ifft_combine");
     IB200_REQUIRE(plan && grid_il && img_out && pf, "null pointer");
     int rc = ensure_device_state(&plan->fft->d);
     if (rc) return rc;
@@ -591,6 +594,32 @@ int ib200_sense_ifft_combine(ib200_sense_plan plan, void *stream, void *img_out,
     a.img_out = (c64 *)img_out; a.pf = (const c64 *)pf; a.grid = (c64 *)grid_il;
     a.alpha = mk(ar, ai); a.beta = mk(br, bi); a.beta_zero = (br == 0.f && bi == 0.f) ? 1 : 0;
     return run_sense_x(s, true, a, plan->fft->d.ax[0].st);
+}
+
+/* One pass of the two fused transforms on its own (same kernels, same arguments as inside
+ * ib200_sense_expand_fft / ib200_sense_ifft_combine), so that a caller can bracket every kernel with events:
+ * which = 0 expand + x pass, 1 forward y, 2 forward z, 3 inverse z, 4 inverse y, 5 x pass + combine. */
+int ib200_sense_pass(ib200_sense_plan plan, void *stream, int which, void *grid_il, const void *img, void *img_out,
+                     const void *pf, float ar, float ai, float br, float bi) {
+    IB200_RANGE("ib200_sense_pass");
+    IB200_REQUIRE(plan && grid_il, "null pointer");
+    IB200_REQUIRE(which >= 0 && which <= 5, "pass index out of range");
+    int rc = ensure_device_state(&plan->fft->d);
+    if (rc) return rc;
+    cudaStream_t s = as_stream(stream);
+    if (which == 0 || which == 5) {
+        SenseFftArgs a;
+        sense_args(plan, &a);
+        a.pf = (const c64 *)pf; a.grid = (c64 *)grid_il;
+        IB200_REQUIRE(pf && (which == 0 ? img != nullptr : img_out != nullptr), "null pointer");
+        if (which == 0) { a.img = (const c64 *)img; return run_sense_x(s, false, a, plan->fft->d.ax[0].st); }
+        a.img_out = (c64 *)img_out;
+        a.alpha = mk(ar, ai); a.beta = mk(br, bi); a.beta_zero = (br == 0.f && bi == 0.f) ? 1 : 0;
+        return run_sense_x(s, true, a, plan->fft->d.ax[0].st);
+    }
+    const bool inverse = which >= 3;
+    const int axis = (which == 1 || which == 4) ? 1 : 2;
+    return sense_strided_pass(plan, s, (c64 *)grid_il, axis, inverse, inverse && axis == 2, !inverse && axis == 2);
 }
 
 }  // extern "C"

@@ -687,6 +687,7 @@ int ib200_cgemm_mode(int mode) {
 
 int ib200_cgemm(void *stream, int conjtrans, int64_t m, int64_t n, int64_t k, float ar, float ai, const void *M,
                 int64_t ldm, const void *X, int64_t ldx, float br, float bi, void *Y, int64_t ldy) {
+    IB200_RANGE("ib200_cgemm");
     IB200_REQUIRE(m >= 0 && n >= 0 && k >= 0, "negative dimension");
     IB200_REQUIRE((M && X) || k == 0 || m == 0 || n == 0, "null pointer");
     IB200_REQUIRE(Y || m == 0 || n == 0, "null Y");

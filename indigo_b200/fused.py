@@ -208,10 +208,33 @@ class SenseDevice(object):
             pass
 
     # ---- the four fused steps ---------------------------------------------------------------
+    # `probe`: optional callable label -> context manager (bench.py's KernelTimer).  When set, the two transforms
+    # are issued pass by pass through ib200_sense_pass (the same kernels with the same arguments) so that every
+    # kernel of the apply can be bracketed by CUDA events.
+    probe = None
+
+    def _step(self, label):
+        import contextlib
+        return self.probe(label) if self.probe is not None else contextlib.nullcontext()
+
     def expand_fft(self, x):
-        self.B._lib.sense_expand_fft(self._plan, self.B._stream, self.grid.ptr, x.ptr, self.pf.ptr)
+        lib, s = self.B._lib, self.B._stream
+        if self.probe is None:
+            lib.sense_expand_fft(self._plan, s, self.grid.ptr, x.ptr, self.pf.ptr)
+            return
+        for which, label in ((0, "sense_expand_pk[x]"), (1, "fft_pass[y fwd]"), (2, "fft_pass[z fwd]")):
+            with self.probe(label):
+                lib.sense_pass(self._plan, s, which, self.grid.ptr, x.ptr, None, self.pf.ptr, 1.0, 0.0, 0.0, 0.0)
 
     def grid_to_samples(self, alpha=1.0):
+        with self._step("kb_gather"):
+            self._grid_to_samples(alpha)
+
+    def samples_to_grid(self):
+        with self._step("csrmm_runs"):
+            self._samples_to_grid()
+
+    def _grid_to_samples(self, alpha=1.0):
         a = complex(alpha)
         G, lib, s = self.G, self.B._lib, self.B._stream
         if self.real and self.kb is not None:
@@ -224,7 +247,7 @@ class SenseDevice(object):
             lib.ccsrmm_il(s, self.M, self.on, self.C, self.nnz, a.real, a.imag, G.values.ptr, G.colInds.ptr,
                           G.rowPtrs.ptr, self.grid.ptr, self.C, self.ksp.ptr, self.C, None, 0, None, 0, 0)
 
-    def samples_to_grid(self):
+    def _samples_to_grid(self):
         lib, s = self.B._lib, self.B._stream
         lr = self.longrows.ptr if self.nlong else None
         if self.real and self.runs is not None:
@@ -243,8 +266,13 @@ class SenseDevice(object):
 
     def ifft_combine(self, y, alpha=1.0, beta=0.0):
         a, b = complex(alpha), complex(beta)
-        self.B._lib.sense_ifft_combine(self._plan, self.B._stream, y.ptr, self.grid.ptr, self.pf.ptr,
-                                       a.real, a.imag, b.real, b.imag)
+        lib, s = self.B._lib, self.B._stream
+        if self.probe is None:
+            lib.sense_ifft_combine(self._plan, s, y.ptr, self.grid.ptr, self.pf.ptr, a.real, a.imag, b.real, b.imag)
+            return
+        for which, label in ((3, "fft_pass[z inv]"), (4, "fft_pass[y inv]"), (5, "sense_combine_pk[x]")):
+            with self.probe(label):
+                lib.sense_pass(self._plan, s, which, self.grid.ptr, None, y.ptr, self.pf.ptr, a.real, a.imag, b.real, b.imag)
 
 
 def make_fused_classes(ops):

@@ -131,6 +131,31 @@ def test_fused_cg_iterates(B):
     assert worst < TOL, worst
 
 
+def test_cg_graph_replay_matches_eager(B):
+    """Whole-iteration CUDA graph (apply + fused solver kernels, one launch per iteration) gives the iterates of the
+    eager loop bit for bit: same kernels, same order, deterministic reductions."""
+    N, C = (16, 16, 16), 4
+    rs, coord, maps, w = _setup(N, C, "koosh", True, seed=9)
+    A = sense_operator_fused(B, N, coord, maps, 2.0, weights=w)
+    AHA = normal_operator(A)
+    x = synth.rand64c(rs, int(np.prod(N)), 1)
+    b = AHA * x
+    b = (b / np.abs(b).max()).astype(C64)
+    xe, xg = np.zeros_like(b, order='F'), np.zeros_like(b, order='F')
+    B.cg(AHA, b, xe, lamda=0.3, maxiter=12, tol=0.0)
+    n0 = B._lib.launch_count()
+    B.cg(AHA, b, xg, lamda=0.3, maxiter=12, tol=0.0, graph=True)
+    np.testing.assert_array_equal(xe, xg)
+    assert np.linalg.norm(xe) > 0
+    # the six-call recipe (generic ccsrmm / fftn kernels, side-stream fork/join) is capturable too
+    Au = sense_operator_device(B, N, coord, maps, 2.0, weights=w)
+    AHAu = normal_operator(Au)
+    xe2, xg2 = np.zeros_like(b, order='F'), np.zeros_like(b, order='F')
+    B.cg(AHAu, b, xe2, lamda=0.3, maxiter=8, tol=0.0)
+    B.cg(AHAu, b, xg2, lamda=0.3, maxiter=8, tol=0.0, graph=True)
+    np.testing.assert_array_equal(xe2, xg2)
+
+
 def test_reduced_cfg4_32_coils_cg(B):
     """BASELINE config 4 at reduced size: 32 coils on one GPU (the fused recipe's maximum), sqrt-DCF rows,
     lamda passed through cg(lamda=) (well-conditioned protocol of DESIGN.md section 5, 0.05 ||A^H A||):

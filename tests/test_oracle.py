@@ -175,3 +175,31 @@ def test_sense_cfg1_structure_digest(golden_dir):
     assert relerr(Ax.ravel(order="F")[sub], g["Ax_sub"]) < 1e-6
     assert abs(np.linalg.norm(Ax) / float(g["Ax_norm"]) - 1) < 1e-6
     assert relerr(op.adjoint(y).ravel(order="F")[sub], g["AHy_sub"]) < 1e-6
+
+
+def test_direct64_matches_the_oracle():
+    """oracle/direct64.py (float64 single-output evaluation used for the full-size GPU checks) against the pinned
+    oracle operator: A x at chosen samples, A^H y at chosen voxels for sparse y; with and without row weights,
+    including samples that sit exactly on a grid line (six taps) and wrap around the grid edge."""
+    from oracle import direct64
+    from indigo_b200 import synth
+    rs = np.random.RandomState(17)
+    N, C = (12, 10, 8), 3
+    coord = synth.random_3d(rs, 120)[:, :, 0]
+    coord[:, 0] = (0.0, 0.25, -0.5)                       # on-grid in every axis, and the wrapped lower edge
+    coord[:, 1] = (0.499, -0.499, 0.0)
+    maps = synth.unit_rss_maps(rs, N, C)
+    x = synth.rand64c(rs, int(np.prod(N)), 1)
+    for w in (None, (0.5 + rs.rand(coord.shape[1])).astype(np.float32)):
+        op = sense.SenseOperator(N, coord, maps, 2.0, weights=w)
+        pick = np.array([0, 1, 5, 17, 63, 119])
+        want = op.forward(x).reshape((op.M, C), order='F')[pick]
+        got = direct64.forward_at_samples(N, coord[:, pick], maps, x, 2.0, weights=None if w is None else w[pick])
+        assert np.linalg.norm(got - want) / np.linalg.norm(want) < 2e-6
+        y = np.zeros((op.M, C), dtype=np.complex64, order='F')
+        y[pick] = synth.rand64c(rs, pick.size, C)
+        full = op.adjoint(np.asfortranarray(y.reshape((-1, 1), order='F'))).reshape(N, order='F')
+        vox = np.array([[0, 0, 0], [11, 9, 7], [6, 5, 4], [3, 8, 1], [10, 0, 6]])
+        got = direct64.adjoint_at_voxels(N, coord[:, pick], y[pick], maps, vox, 2.0, weights=None if w is None else w[pick])
+        want = full[vox[:, 0], vox[:, 1], vox[:, 2]]
+        assert np.linalg.norm(got - want) / np.linalg.norm(want) < 2e-6
