@@ -388,6 +388,42 @@ static int exec_impl(FftPlanData *pl, cudaStream_t s, c64 *y, const c64 *x, int 
 
 using namespace ib200;
 
+// z axis of at most kTinyAxis points (2-D problems carried as N0 x N1 x 1 images: cfg1's grid is 512 x 512 x 2):
+// the "transform" is a handful of complex adds per (y, x, coil) line, done directly by one thread per line, in
+// place.  Forward: out[k] = sum_{j in window} in[j] e^{-2 pi i jk/n}.  Inverse: this is the FIRST pass of the
+// inverse chain, whose later passes run forward transforms on (im, re)-swapped data (conjugation trick), so it
+// stores swap(sum_k in[k] e^{+2 pi i jk/n}) for the output window j only.
+static const int kTinyAxis = 8;
+
+template <bool INV>
+__global__ void __launch_bounds__(256) sense_tiny_z_kernel(c64 *__restrict__ grid, int64_t plane, int n, int w0, int w1) {
+    c64 tw[kTinyAxis];
+    for (int m = 0; m < n; ++m) {
+        double sn, cs;
+        sincospi(2.0 * (double)m / (double)n, &sn, &cs);
+        tw[m] = mk((float)cs, (float)(INV ? sn : -sn));
+    }
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += nth) {
+        c64 v[kTinyAxis];
+        if (!INV) {
+            for (int j = w0; j < w1; ++j) v[j - w0] = grid[(int64_t)j * plane + i];
+            for (int k = 0; k < n; ++k) {
+                c64 acc = mk(0.f, 0.f);
+                for (int j = w0; j < w1; ++j) acc = cfma(v[j - w0], tw[(j * k) % n], acc);
+                grid[(int64_t)k * plane + i] = acc;
+            }
+        } else {
+            for (int k = 0; k < n; ++k) v[k] = grid[(int64_t)k * plane + i];
+            for (int j = w0; j < w1; ++j) {
+                c64 acc = mk(0.f, 0.f);
+                for (int k = 0; k < n; ++k) acc = cfma(v[k], tw[(j * k) % n], acc);
+                grid[(int64_t)j * plane + i] = cswap(acc);
+            }
+        }
+    }
+}
+
 extern "C" {
 
 int ib200_fft_plan_create(ib200_fft_plan *plan, int ndim, const int64_t *dims, int64_t batch) {
@@ -459,6 +495,17 @@ static bool sense_z_pass_is_persistent(const ib200_sense_plan_s *p) {
 
 static int sense_strided_pass(ib200_sense_plan_s *p, cudaStream_t s, c64 *grid, int axis, bool inverse, bool first,
                               bool last) {
+    if (axis == 2 && p->oN[2] <= kTinyAxis) {
+        const int64_t plane = p->oN[0] * p->C * p->oN[1];
+        const int w0 = (int)p->off[2], w1 = (int)(p->off[2] + p->N[2]);
+        int64_t blocks = ceil_div(plane, 256 * 4);
+        const int64_t cap = (int64_t)sm_count() * 16;
+        if (blocks > cap) blocks = cap;
+        if (inverse) sense_tiny_z_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(grid, plane, (int)p->oN[2], w0, w1);
+        else         sense_tiny_z_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(grid, plane, (int)p->oN[2], w0, w1);
+        IB200_LAUNCH_CHECK();
+        return 0;
+    }
     // axis 1: lines are the (x, c) pairs of one y row, one slab per z of the image window;
     // axis 2: lines are all (y, x, c) triples, a single slab.
     const FftPlanData &pl = p->fft->d;
@@ -514,7 +561,7 @@ int ib200_sense_plan_create(ib200_sense_plan *plan, const int64_t N[3], const in
         p->N[d] = N[d]; p->oN[d] = oN[d];
         p->off[d] = oN[d] / 2 - N[d] / 2;                       // Zpad 'center': oN//2 + ceil(-N/2), backend.py:379-381
         FftKernelArgs k; k.n = (int)oN[d]; k.st = p->fft->d.ax[d].st;
-        bool ok = false;
+        bool ok = d == 2 && oN[d] <= kTinyAxis;                 // tiny z axis: direct pass (sense_tiny_z_kernel)
 #define IB200_SENSE_OK(n, r0, r1, r2) ok = ok || fft_spec_matches(k, n, r0, r1, r2);
         IB200_FFT_SPEC_LIST(IB200_SENSE_OK)
 #undef IB200_SENSE_OK

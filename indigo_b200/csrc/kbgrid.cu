@@ -83,70 +83,49 @@ __global__ void __launch_bounds__(128) kb_records_kernel(int64_t m, const double
     rec[r] = q;
 }
 
-// VC coils per lane as packed (re, im) pairs: one 8-byte or one 16-byte load per tap, no unpacking
+// (A packed-FFMA2 form of this row sum with incrementally stepped row pointers was measured in round 2,
+// profiles/r02_s2_cfg3.md: 14 % fewer warp instructions but IPC 2.0 -> 1.5 and 5.0 -> 5.9 ms at cfg3 -- the scalar
+// form below lets ptxas hoist the next row's loads over this row's FMAs within the 64-register budget.)
+// VC coils per lane: one 8-byte or one 16-byte load per tap
 template <int VC> struct KbVec;
 template <> struct KbVec<1> {
-    pk2 c[1];
-    __device__ __forceinline__ void load(const char *p) {
-#ifdef __CUDA_ARCH__
-        c[0].v = __ldg(reinterpret_cast<const unsigned long long *>(p));
-#endif
-    }
+    float x[1], y[1];
+    __device__ __forceinline__ void load(const char *p) { const float2 v = __ldg(reinterpret_cast<const float2 *>(p)); x[0] = v.x; y[0] = v.y; }
 };
 template <> struct KbVec<2> {
-    pk2 c[2];
+    float x[2], y[2];
     __device__ __forceinline__ void load(const char *p) {
-#ifdef __CUDA_ARCH__
-        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(p));
-        c[0].v = v.x; c[1].v = v.y;
-#endif
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(p)); x[0] = v.x; y[0] = v.y; x[1] = v.z; y[1] = v.w;
     }
 };
 
 // one (z, y) row of taps: weighted sum over the x taps, folded into the accumulator with wjk = wz*wy.
-// Packed arithmetic: a complex value is one (re, im) register pair, a real weight multiplies both halves in
-// one FFMA2 (half the issue slots of the scalar form; the kernel was issue-bound at IPC 2.0,
-// profiles/r01_s9_final_cfg3.md).  The order of the operations is the scalar one: bit-identical results.
 // DENSE: the x taps are consecutive grid points (no wrap-around in this warp) and the pitch of a
 // grid point is the compile-time constant PITCH, so the tap addresses are immediates.
 template <int VC, bool DENSE, int PITCH>
 __device__ __forceinline__ void kb_row(const char *rp, const uint32_t (&xo)[kKbTaps], const float (&wx)[kKbTaps],
-                                       bool sixth, float wjk, pk2 (&acc)[VC]) {
+                                       bool sixth, float wjk, float (&ax)[VC], float (&ay)[VC]) {
     KbVec<VC> q[kKbTaps];
     const char *r0 = rp + xo[0];
 #pragma unroll
     for (int t = 0; t < kKbTaps - 1; ++t) q[t].load(DENSE ? r0 + t * PITCH : rp + xo[t]);
-    pk2 tsum[VC];
+    float tx[VC], ty[VC];
 #pragma unroll
-    for (int v = 0; v < VC; ++v) tsum[v] = p_scale(wx[0], q[0].c[v]);
+    for (int v = 0; v < VC; ++v) { tx[v] = wx[0] * q[0].x[v]; ty[v] = wx[0] * q[0].y[v]; }
 #pragma unroll
     for (int t = 1; t < kKbTaps - 1; ++t)
 #pragma unroll
-        for (int v = 0; v < VC; ++v) tsum[v] = p_fmac(wx[t], q[t].c[v], tsum[v]);
+        for (int v = 0; v < VC; ++v) { tx[v] = fmaf(wx[t], q[t].x[v], tx[v]); ty[v] = fmaf(wx[t], q[t].y[v], ty[v]); }
     if (sixth) {                                                     // warp-uniform, rare
         q[kKbTaps - 1].load(DENSE ? r0 + (kKbTaps - 1) * PITCH : rp + xo[kKbTaps - 1]);
 #pragma unroll
-        for (int v = 0; v < VC; ++v) tsum[v] = p_fmac(wx[kKbTaps - 1], q[kKbTaps - 1].c[v], tsum[v]);
-    }
-#pragma unroll
-    for (int v = 0; v < VC; ++v) acc[v] = p_fmac(wjk, tsum[v], acc[v]);
-}
-
-// the rows of one z plane: row pointers advance by adds (a wrap-around in y is a warp-uniform rare case)
-template <int VC, bool DENSE, int PITCH>
-__device__ __forceinline__ void kb_plane(const char *zp, uint64_t rowbytes, int iy0, int n1, int nym, bool ynowrap,
-                                         const uint32_t (&xo)[kKbTaps], const float (&wx)[kKbTaps],
-                                         const float (&wy)[kKbTaps], bool sixth, float wk, pk2 (&acc)[VC]) {
-    const char *rp = zp + (uint64_t)iy0 * rowbytes;
-    int iy = iy0;
-#pragma unroll
-    for (int j = 0; j < kKbTaps; ++j) {
-        if (j < nym) {                                               // warp-uniform
-            kb_row<VC, DENSE, PITCH>(rp, xo, wx, sixth, wk * wy[j], acc);
-            rp += rowbytes;
-            if (!ynowrap) { if (++iy >= n1) { iy = 0; rp = zp; } }
+        for (int v = 0; v < VC; ++v) {
+            tx[v] = fmaf(wx[kKbTaps - 1], q[kKbTaps - 1].x[v], tx[v]);
+            ty[v] = fmaf(wx[kKbTaps - 1], q[kKbTaps - 1].y[v], ty[v]);
         }
     }
+#pragma unroll
+    for (int v = 0; v < VC; ++v) { ax[v] = fmaf(wjk, tx[v], ax[v]); ay[v] = fmaf(wjk, ty[v], ay[v]); }
 }
 
 // Y[out(r)*ypitch + c] = alpha * sum_{k,j,i} wz[k] wy[j] wx[i] * grid[iz_k][iy_j][ix_i][c]
@@ -170,7 +149,6 @@ __global__ void __launch_bounds__(256, 4) kb_gather_kernel(int64_t m, int C, c64
     const bool coil_ok = coil < C;
     const char *gb = reinterpret_cast<const char *>(grid + (coil_ok ? coil : 0));
     const uint64_t rowbytes = (uint64_t)n0 * pitch;
-    const uint64_t planebytes = rowbytes * (uint64_t)n1;
     const bool dense_pitch = pitch == (uint32_t)PITCH;
     // the 8 warps of the CTA sweep its records together (32 consecutive samples per step): what is in L1
     // at any time is the footprint of one or two neighbouring tiles, not of 8 unrelated ones
@@ -201,35 +179,49 @@ __global__ void __launch_bounds__(256, 4) kb_gather_kernel(int64_t m, int C, c64
                   nzm = __reduce_max_sync(FULL, (nt >> 16) & 255);
         const bool sixth = nxm > kKbTaps - 1;
         const bool dense = dense_pitch && __all_sync(FULL, ix0 + kKbTaps <= n0);
-        const bool ynowrap = __all_sync(FULL, iy0 + kKbTaps <= n1);
         uint32_t xo[kKbTaps];
         {
             int j = ix0;
 #pragma unroll
             for (int t = 0; t < kKbTaps; ++t) { xo[t] = (uint32_t)j * pitch; if (++j >= n0) j = 0; }
         }
-        pk2 acc[VC];
+        float ax[VC], ay[VC];
 #pragma unroll
-        for (int v = 0; v < VC; ++v) acc[v] = p_make(0.f, 0.f);
+        for (int v = 0; v < VC; ++v) { ax[v] = 0.f; ay[v] = 0.f; }
         int iz = iz0;
-        const char *zp = gb + (uint64_t)iz0 * planebytes;
         for (int k = 0; k < nzm; ++k) {
             const float wk = wz[0];
 #pragma unroll
             for (int t = 0; t < kKbTaps - 1; ++t) wz[t] = wz[t + 1];
             wz[kKbTaps - 1] = 0.f;
-            if (dense) kb_plane<VC, true, PITCH>(zp, rowbytes, iy0, n1, nym, ynowrap, xo, wx, wy, sixth, wk, acc);
-            else       kb_plane<VC, false, PITCH>(zp, rowbytes, iy0, n1, nym, ynowrap, xo, wx, wy, sixth, wk, acc);
-            zp += planebytes;
-            if (++iz >= n2) { iz = 0; zp = gb; }
+            const uint64_t zrow = (uint64_t)iz * (uint64_t)n1;
+            int iy = iy0;
+            if (dense) {
+#pragma unroll
+                for (int j = 0; j < kKbTaps; ++j) {
+                    if (j < nym) {                                   // warp-uniform
+                        kb_row<VC, true, PITCH>(gb + (zrow + (uint64_t)iy) * rowbytes, xo, wx, sixth, wk * wy[j], ax, ay);
+                        if (++iy >= n1) iy = 0;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < kKbTaps; ++j) {
+                    if (j < nym) {
+                        kb_row<VC, false, PITCH>(gb + (zrow + (uint64_t)iy) * rowbytes, xo, wx, sixth, wk * wy[j], ax, ay);
+                        if (++iy >= n1) iy = 0;
+                    }
+                }
+            }
+            if (++iz >= n2) iz = 0;
         }
         if (out >= 0 && coil_ok) {
             c64 *yp = Y + (int64_t)out * ypitch + coil;
             if (VC == 2) {
-                const c64 o0 = cmul(alpha, mk(p_lo(acc[0]), p_hi(acc[0]))), o1 = cmul(alpha, mk(p_lo(acc[VC - 1]), p_hi(acc[VC - 1])));
+                const c64 o0 = cmul(alpha, mk(ax[0], ay[0])), o1 = cmul(alpha, mk(ax[VC - 1], ay[VC - 1]));
                 __stcs(reinterpret_cast<float4 *>(yp), make_float4(o0.x, o0.y, o1.x, o1.y));
             } else {
-                __stcs(yp, cmul(alpha, mk(p_lo(acc[0]), p_hi(acc[0]))));
+                __stcs(yp, cmul(alpha, mk(ax[0], ay[0])));
             }
         }
     }

@@ -228,6 +228,48 @@ def test_fused_matches_six_call_tree_at_size(B):
     assert abs(lhs - rhs) / abs(lhs) < TOL
 
 
+@pytest.mark.parametrize("C", [8, 2])
+def test_fused_two_dimensional_problem(B, C):
+    """2-D problems are carried as N0 x N1 x 1 images (the reference's NUFFT is 3-D only, backend.py:404-405): the
+    oversampled grid has a z axis of two points, served by the direct tiny-axis pass; the Kaiser-Bessel taps alias
+    onto the two planes, so the gridding steps run on stored entries (no separable records)."""
+    N = (16, 16, 1)
+    rs = np.random.RandomState(40 + C)
+    coord = synth.radial_2d(nspokes=24, nread=32)
+    maps = synth.unit_rss_maps(rs, N, C)
+    A = sense_operator_fused(B, N, coord, maps, 2.0)
+    assert A._dev.oN == (32, 32, 2) and A._dev.kb is None
+    ref = osense.SenseOperator(N, coord, maps, 2.0)
+    x = synth.rand64c(rs, int(np.prod(N)), 1)
+    y = synth.rand64c(rs, ref.M * C, 1)
+    assert relerr(A * x, ref.forward(x)) < TOL
+    assert relerr(A.H * y, ref.adjoint(y)) < TOL
+    assert relerr(normal_operator(A) * x, ref.normal(x)) < TOL
+
+
+def test_cfg1_full_size_fused(B, golden_dir):
+    """BASELINE configs[0] at full size through the fused recipe, against the digest of the unmodified reference's
+    NumpyBackend (tests/golden/make_golden.py): 256 x 256 x 1 image, grid 512 x 512 x 2, 8 coils, 402 spokes x 512."""
+    import os
+    g = np.load(os.path.join(golden_dir, "sense_cfg1_digest.npz"))
+    N, C = tuple(int(v) for v in g["N"]), int(g["C"])
+    rs = np.random.RandomState(int(g["seed"]))
+    maps = synth.unit_rss_maps(rs, N, C)
+    coord = synth.radial_2d(402, 512)
+    A = sense_operator_fused(B, N, coord, maps, float(g["oversamp"]))
+    x = synth.rand64c(rs, int(np.prod(N)), 1)
+    y = synth.rand64c(rs, coord.shape[1] * coord.shape[2] * C, 1)
+    sub = slice(None, None, 997)
+    Ax = A * x
+    assert relerr(Ax.ravel(order='F')[sub], g["Ax_sub"]) < TOL
+    assert abs(np.linalg.norm(Ax) / float(g["Ax_norm"]) - 1) < TOL
+    AHy = A.H * y
+    assert relerr(AHy.ravel(order='F')[sub], g["AHy_sub"]) < TOL
+    AHAx = normal_operator(A) * x
+    assert relerr(AHAx.ravel(order='F')[sub], g["AHAx_sub"]) < TOL
+    assert abs(np.linalg.norm(AHAx) / float(g["AHAx_norm"]) - 1) < TOL
+
+
 def test_fused_refuses_unsupported_grid(B):
     N, C = (11, 12, 13), 2                       # 22 x 24 x 26: no specialised passes
     rs, coord, maps, w = _setup(N, C, "random", False)

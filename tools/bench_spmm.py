@@ -27,6 +27,9 @@ def main():
     args = ap.parse_args()
     peak, src = bench.peaks()
     B = B200Backend(0)
+    L2 = torch.cuda.get_device_properties(0).L2_cache_size
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    clock = 1.965e9
     C64 = np.dtype("complex64")
     rows = cols = args.rows
     print("# cfg2: random complex64 CSR SpMM sweep, %d x %d, through Backend.csr_matrix.forward/.adjoint" % (rows, cols))
@@ -35,8 +38,14 @@ def main():
     print("Multi-column products take the coil-interleaved path (interleave -> gather -> deinterleave, 3 launches);")
     print("adjoints use the stored conjugate transpose (built once on the device, not timed).  Median of %d, CUDA events." % args.reps)
     print()
-    print("| nnz/row | ncols | fwd ms | fwd GB/s | fwd frac | adj ms | adj GB/s | adj frac |")
-    print("|---:|---:|---:|---:|---:|---:|---:|---:|")
+    print("`gather floor`: what uniformly random columns cost on this memory system, which the one-pass figure of 8(d) leaves")
+    print("out: every stored entry pulls ceil(8*ncols/32) 32-byte sectors of X; X (8*ncols*cols bytes) exceeds the %d MB L2" % (L2 >> 20))
+    print("from 16 columns on, so a fraction 1 - L2/|X| of those sectors comes from DRAM; and every gather is one L1")
+    print("wavefront per 128 bytes (1 wavefront/cycle/SM).  floor = max(8(d) bytes / peak, matrix + gathered DRAM sectors")
+    print("/ peak, wavefronts / (SMs * clock)); `vs floor` = floor / measured.")
+    print()
+    print("| nnz/row | ncols | fwd ms | fwd GB/s | fwd frac | adj ms | adj GB/s | adj frac | gather floor ms | fwd vs floor |")
+    print("|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
 
     def timed(fn):
         fn(); torch.cuda.synchronize()
@@ -59,8 +68,14 @@ def main():
             tf = timed(lambda: Ad.forward(y, x))
             ta = timed(lambda: Ad.adjoint(yt, xt))
             alg = 12 * A.nnz + 4 * (rows + 1) + 8 * n * (rows + cols)
-            print("| %d | %d | %.3f | %.0f | %.2f | %.3f | %.0f | %.2f |" % (
-                r, n, tf, alg / tf / 1e6, alg / tf / 1e6 / peak, ta, alg / ta / 1e6, alg / ta / 1e6 / peak))
+            xbytes = 8.0 * n * cols
+            sect = -(-8 * n // 32) * 32
+            miss = max(0.0, 1.0 - L2 / xbytes)
+            dram = 12.0 * A.nnz + A.nnz * sect * miss + xbytes * min(1.0, 1.0 - miss + 1e-9) + 8.0 * n * rows
+            wavefronts = A.nnz * (-(-8 * n // 128))
+            floor = max(alg / peak / 1e6, dram / peak / 1e6, wavefronts / (sms * clock) * 1e3)
+            print("| %d | %d | %.3f | %.0f | %.2f | %.3f | %.0f | %.2f | %.3f | %.2f |" % (
+                r, n, tf, alg / tf / 1e6, alg / tf / 1e6 / peak, ta, alg / ta / 1e6, alg / ta / 1e6 / peak, floor, floor / tf))
             sys.stdout.flush()
             del x, y, xt, yt
         del Ad
