@@ -297,7 +297,10 @@ static int launch_sense_x_pk(cudaStream_t s, bool combine, const SenseFftArgs &a
     static bool attr_done[2][64] = {{false}};
     if (!pk_enabled() || (a.C & 1)) return -100;
     if (((uintptr_t)a.grid & 15) || ((uintptr_t)a.pf & 15)) return -100;
-    const size_t smem = combine ? pk_smem_floats(N, R2 > 1, true) * sizeof(float) + (size_t)a.N0 * sense_x_tile(a.C).YY * sizeof(c64)
+    // the cross-chunk accumulators of the coil fold are only needed with more than one 16-coil chunk; without them a
+    // 2-coil operator (8 image rows per tile) keeps two CTAs per SM (r02: 12.5 % occupancy, 0.52 ms with them)
+    const size_t accb = a.C > kSpecL ? (size_t)a.N0 * sense_x_tile(a.C).YY * sizeof(c64) : 0;
+    const size_t smem = combine ? pk_smem_floats(N, R2 > 1, true) * sizeof(float) + accb
                                 : pk_smem_floats(N, R2 > 1, false) * sizeof(float);
     if ((int64_t)smem > smem_optin()) return -100;
     int dev = 0;

@@ -580,6 +580,7 @@ IB_HD void sense_combine_pk_body(const SenseFftArgs &a, float *bufA, c64 *acc, i
         IB_SYNC();
         const float *re = c.res, *im = c.res + c.resplane;
         const int np = ncl / 2;
+        const bool single = a.C <= kSpecL;                         // one coil chunk: the fold goes straight to the image
         for (int i = tid; i < rows * a.N0; i += nt) {
             const int yy = i / a.N0, j = i - yy * a.N0;
             const float *pr = re + j * kSpecL + yy * ncl, *pi = im + j * kSpecL + yy * ncl;
@@ -590,10 +591,17 @@ IB_HD void sense_combine_pk_body(const SenseFftArgs &a, float *bufA, c64 *acc, i
                 sy += pi[2 * p] + pi[2 * p + 1];
                 if (++p == np) p = 0;
             }
-            acc[i] = c0 == 0 ? h_mk(sx, sy) : h_add(acc[i], h_mk(sx, sy));
+            if (single) {
+                c64 v = h_mul(a.alpha, h_mk(sx, sy));
+                if (!a.beta_zero) v = h_add(v, h_mul(a.beta, a.img_out[vox0 + i]));
+                a.img_out[vox0 + i] = v;
+            } else {
+                acc[i] = c0 == 0 ? h_mk(sx, sy) : h_add(acc[i], h_mk(sx, sy));
+            }
         }
         IB_SYNC();
     }
+    if (a.C <= kSpecL) return;
     for (int i = tid; i < rows * a.N0; i += nt) {
         c64 v = h_mul(a.alpha, acc[i]);
         if (!a.beta_zero) v = h_add(v, h_mul(a.beta, a.img_out[vox0 + i]));

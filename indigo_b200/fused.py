@@ -58,6 +58,10 @@ class SenseDevice(object):
             self.sample_tile = (int(os.environ["IB200_SAMPLE_TILE"]),) * 3
         if os.environ.get("IB200_RUN_LONG"):                        # tuning knob (tools/): run-length threshold
             self.run_long_thresh = int(os.environ["IB200_RUN_LONG"])
+        elif int(np.prod(np.asarray(coord).shape[1:])) < (1 << 20) and type(self).run_long_thresh == 1024:
+            # small problems (cfg1: 0.2 M samples) are bound by the longest serial walk of one lane group, not by
+            # throughput: cut dense runs into shorter segments (r02 session 3: adjoint step 0.17 ms of a 0.37 ms apply)
+            self.run_long_thresh = 256
         from .kbmath import rolloff3
 
         self.B = B
