@@ -141,6 +141,8 @@ def fused_kernel_bytes(dev):
     inside = dev.support_fraction * on                       # grid points inside the k-space support windows
     px, py = oN[0] * N[1] * N[2], oN[0] * oN[1] * N[2]       # points per coil after the x pass / the y pass
     ent = dev.runs['entries'] * 20 if dev.runs is not None else dev.nnz * 8
+    tiles = getattr(dev, 'tiles', None)
+    tent = tiles['bytes'] if tiles is not None else 0
     nnzb = dev.nnz * 12
     ccs_G = nnzb + 4 * (M + 1) + 8 * C * (on + M)            # ccsrmm(G'), each operand once
     ccs_GH = nnzb + 4 * (M + 1) + 8 * C * (M + on)
@@ -154,6 +156,7 @@ def fused_kernel_bytes(dev):
         "fft_pass[z fwd]": (8 * C * (py + inside), third, "fftn/3"),
         "kb_gather": (8 * C * inside + 96 * M + 8 * C * M, ccs_G, "ccsrmm(G')"),
         "csrmm_runs": (ent + 8 * C * M + 8 * C * inside, ccs_GH, "ccsrmm(G',adj)"),
+        "kb_tiles": (tent + 8 * C * M + 8 * C * inside, ccs_GH, "ccsrmm(G',adj)"),
         "fft_pass[z inv]": (8 * C * (inside + py), third, "ifftn/3"),
         "fft_pass[y inv]": (8 * C * (py + px), third, "ifftn/3"),
         "sense_combine_pk[x]": (8 * C * px + 8 * nvox * C + 8 * nvox, ccs_PH + third, "ifftn/3 + ccsrmm(P^H)"),

@@ -5,6 +5,18 @@
 
 namespace ib200 {
 
+// separable-weight record of one sample (kbgrid.cu builds them; kbgrid.cu and kbtiles.cu read them)
+static const int kKbTaps = 6;
+
+struct __align__(16) KbRecord {
+    float wx[kKbTaps], wy[kKbTaps], wz[kKbTaps];   // per-axis weights (row weight and scale folded into wz)
+    int32_t ix0, iy0, iz0;                         // first tap per axis, wrapped into [0, n)
+    int32_t out;                                   // output row (original sample index)
+    int32_t ntaps;                                 // nx | ny << 8 | nz << 16
+    int32_t pad;
+};
+static_assert(sizeof(KbRecord) == 96, "KbRecord must be 6 x 16 bytes");
+
 // interp.py:9-15 (lin_interp) with every operation individually rounded
 __device__ __forceinline__ double kb_lookup(const double *__restrict__ table, int ntab, double x) {
     if (x >= 1.0) return 0.0;

@@ -23,17 +23,6 @@
 
 namespace ib200 {
 
-static const int kKbTaps = 6;
-
-struct __align__(16) KbRecord {
-    float wx[kKbTaps], wy[kKbTaps], wz[kKbTaps];   // per-axis weights (row weight and scale folded into wz)
-    int32_t ix0, iy0, iz0;                         // first tap per axis, wrapped into [0, n)
-    int32_t out;                                   // output row (original sample index)
-    int32_t ntaps;                                 // nx | ny << 8 | nz << 16
-    int32_t pad;
-};
-static_assert(sizeof(KbRecord) == 96, "KbRecord must be 6 x 16 bytes");
-
 // record r describes sample perm[r] (perm = NULL: identity)
 __global__ void __launch_bounds__(128) kb_records_kernel(int64_t m, const double *__restrict__ coord, int N0, int N1,
                                                          int N2, double width, const double *__restrict__ table,

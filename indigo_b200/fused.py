@@ -46,6 +46,10 @@ class SenseDevice(object):
     allow_sorted_ksp = True    # keep k-space in tile-sorted sample order between the two gridding steps
     allow_runs = True          # adjoint gridding on merged x-runs of the stored adjoint (csrc/csrmm_runs.cu)
     run_long_thresh = 1024     # runs with more entries than this are cut into segments of this length
+    allow_tiles = True         # adjoint gridding on tile-block entries (csrc/kbtiles.cu) when the coils are few
+    tiles_max_coils = 4        # ... i.e. at most this many (coil-sharded operators; the x-runs win above)
+    tiles_seg_batches = 64     # tiles with more batches (of 4 entries) than this are cut into work items of this length
+    tiles_lanes = 0            # lanes sharing the 64 points of a tile (0: kernel default)
     allow_windows = True       # k-space support windows: skip the grid outside the trajectory's support
     window_min_saving = 0.05   # ... when at least this fraction of the grid lies outside
 
@@ -56,6 +60,10 @@ class SenseDevice(object):
             self.sample_super = (int(os.environ["IB200_SAMPLE_SUPER"]),) * 3
         if os.environ.get("IB200_SAMPLE_TILE"):                     # tuning knob: sample tile edge in grid points
             self.sample_tile = (int(os.environ["IB200_SAMPLE_TILE"]),) * 3
+        if os.environ.get("IB200_TILES_MAXC"):                      # tuning knobs (tools/): tile-block adjoint gather
+            self.tiles_max_coils = int(os.environ["IB200_TILES_MAXC"])
+        if os.environ.get("IB200_TILES_SEG"):
+            self.tiles_seg_batches = int(os.environ["IB200_TILES_SEG"])
         if os.environ.get("IB200_RUN_LONG"):                        # tuning knob (tools/): run-length threshold
             self.run_long_thresh = int(os.environ["IB200_RUN_LONG"])
         elif int(np.prod(np.asarray(coord).shape[1:])) < (1 << 20) and type(self).run_long_thresh == 1024:
@@ -137,7 +145,8 @@ class SenseDevice(object):
                 # are then neighbours in memory (the original spoke order scatters them over 0.9 GB at cfg3)
                 self.kb = None
                 use_runs = self.allow_runs and C % 2 == 0 and self.tile[0] == 4 and kp % 4 == 0
-                self.ksp_sorted = bool(self.allow_separable and use_runs and self.allow_sorted_ksp)
+                use_tiles = self._want_tiles()
+                self.ksp_sorted = bool(self.allow_separable and (use_runs or use_tiles) and self.allow_sorted_ksp)
                 if self.allow_separable:
                     self.kb = kb_records_device(B, self.oN, coord, beta, weights, width, n, perm=self.g_map,
                                                 out_sorted=self.ksp_sorted)
@@ -177,10 +186,33 @@ class SenseDevice(object):
                         self.win, self.rowmap, self.support_fraction = win, rowmap_w, frac
                     except RuntimeError:
                         pass                                            # geometry without persistent packed z passes
+        # few coils (the shard of a coil-sharded operator): tile-block entries built from the separable records, one
+        # 52-byte entry and one gather per (sample, 4x4x4 tile) pair instead of 6.75 run entries (csrc/kbtiles.cu)
+        self.tiles = None
+        if self.real and self.kb is not None and self._want_tiles():
+            segb = max(1, int(self.tiles_seg_batches))
+            ntile = kp // 64
+            bptr = B.empty_array((ntile + 1,), i32, name='G.H.tiles.batchptr')
+            wptr = B.empty_array((ntile + 1,), i32, name='G.H.tiles.workptr')
+            tot = (ctypes.c_int64 * 5)()
+            lib.kb_tiles_count(s, self.M, self.kb.ptr, grid3, self.rowmap.ptr, segb, bptr.ptr, wptr.ptr, tot)
+            nbat, nwork, nsplit, nslot = int(tot[1]), int(tot[2]), int(tot[3]), int(tot[4])
+            bb = int(lib.kb_tiles_batch_bytes())
+            ent = B.empty_array((max(nbat, 1) * bb // 16 * 2,), np.dtype('int64'), name='G.H.tiles.entries')
+            work = B.empty_array((4 * max(nwork, 1),), i32, name='G.H.tiles.work')
+            split = B.empty_array((4 * max(nsplit, 1),), i32, name='G.H.tiles.split')
+            lib.kb_tiles_fill(s, self.M, self.kb.ptr, grid3, segb, bptr.ptr, wptr.ptr, ent.ptr, work.ptr, split.ptr)
+            cl = 1
+            while cl < C // 2:
+                cl *= 2
+            scratch = B.empty_array((max(nslot, 1) * 64 * 2 * cl,), _C64, name='G.H.tiles.partial')
+            self.tiles = dict(ent=ent, work=work, nwork=nwork, split=split, nsplit=nsplit, scratch=scratch,
+                              batches=nbat, bytes=nbat * bb)
+            del bptr, wptr
         # x-run lists of the stored adjoint: one gather of a sample serves the four grid points of a tile row;
         # runs longer than run_long_thresh entries are cut into segments with their own lane groups
         self.runs = None
-        if self.real and self.allow_runs and C % 2 == 0 and self.tile[0] == 4 and kp % 4 == 0:
+        if self.tiles is None and self.real and self.allow_runs and C % 2 == 0 and self.tile[0] == 4 and kp % 4 == 0:
             seg = max(4, int(self.run_long_thresh) // 4 * 4)
             run_ptr = B.empty_array((kp // 4 + 1,), i32, name='G.H.runs.ptr')
             nre, nsg, nsp = ctypes.c_int64(), ctypes.c_int(), ctypes.c_int()
@@ -203,6 +235,10 @@ class SenseDevice(object):
         # multiplies its zero-weight taps (6th tap of on-grid samples) with whatever is there
         self.grid = B.zero_array((self.on * C,), _C64, name='grid[z][y][x][c]')
         self.ksp = B.empty_array((self.M * C,), _C64, name='ksp[m][c]')
+
+    def _want_tiles(self):
+        return bool(self.allow_tiles and self.allow_separable and self.C % 2 == 0 and self.C <= self.tiles_max_coils
+                    and self.C <= 8 and tuple(self.tile) == (4, 4, 4))
 
     def __del__(self):
         try:
@@ -235,7 +271,7 @@ class SenseDevice(object):
             self._grid_to_samples(alpha)
 
     def samples_to_grid(self):
-        with self._step("csrmm_runs"):
+        with self._step("kb_tiles" if self.tiles is not None else "csrmm_runs"):
             self._samples_to_grid()
 
     def _grid_to_samples(self, alpha=1.0):
@@ -254,7 +290,12 @@ class SenseDevice(object):
     def _samples_to_grid(self):
         lib, s = self.B._lib, self.B._stream
         lr = self.longrows.ptr if self.nlong else None
-        if self.real and self.runs is not None:
+        if self.real and self.tiles is not None:
+            t = self.tiles
+            lib.kb_tiles_apply(s, self.C, 1.0, 0.0, t['nwork'], t['work'].ptr, t['ent'].ptr, self.ksp.ptr, self.C,
+                               self.grid.ptr, self.C, self.rowmap.ptr, t['nsplit'], t['split'].ptr, t['scratch'].ptr,
+                               int(self.tiles_lanes))
+        elif self.real and self.runs is not None:
             r = self.runs
             lib.ccsrmm_runs(s, self.kp, self.C, 1.0, 0.0, r['ptr'].ptr, r['ids'].ptr, r['w4'].ptr, self.ksp.ptr, self.C,
                             self.grid.ptr, self.C, self.rowmap.ptr, r['seg'], r['segd'].ptr, r['nseg'], r['spld'].ptr,
