@@ -216,8 +216,9 @@ int ib200_ccsrmm_runs(void *stream, int64_t kp, int64_t ncols, float alpha_re, f
  *     overwritten with zeros on every apply).
  *   ib200_kb_tiles_fill: writes entries[batches * batch_bytes], work[4 * work items], split[4 * split tiles].
  *   ib200_kb_tiles_apply: Yil[rowmap[64*t + p]][c] = alpha * sum_e wz_e[pz] wy_e[py] wx_e[px] * Xil[out(e)][c]
- *     for an even number of at most 8 interleaved columns; scratch: (work items of split tiles) * 64 *
- *     2*pow2ceil(ncols/2) complex words; lanes: 0 or the number of lanes (4, 8, 16) that share the points of a tile.
+ *     for an even number of at most 64 interleaved columns (served in chunks of 16); scratch: (work items of
+ *     split tiles) * 64 * 2*pow2ceil(min(ncols,16)/2) complex words; lanes: 0 or the number of lanes (4, 8, 16)
+ *     that share the points of a tile.
  * The first two synchronise. */
 int ib200_kb_tiles_batch_bytes(void);
 int ib200_kb_tiles_count(void *stream, int64_t m, const void *records, const int64_t grid[3], const int32_t *rowmap,

@@ -72,6 +72,14 @@ __device__ __forceinline__ void record_tiles(const KbRecord &q, int n0, int n1, 
     axis_tiles(q.iz0, (q.ntaps >> 16) & 255, n2, q.wz, az);
 }
 
+// work items of a tile with nb batches: segments of seg_batches batches, lengthened for the densest tiles so that no
+// tile has more than kTMaxSeg of them (the fold of a tile's partial sums is a serial chain over its segments)
+static const int kTMaxSeg = 48;
+__host__ __device__ __forceinline__ int tile_seg_len(int nb, int seg_batches) {
+    const int cap = (nb + kTMaxSeg - 1) / kTMaxSeg;
+    return cap > seg_batches ? cap : seg_batches;
+}
+
 // pairs per record (rcnt) and per tile (tcnt)
 __global__ void __launch_bounds__(128) tile_pairs_count_kernel(int64_t m, const KbRecord *__restrict__ rec, int n0, int n1,
                                                                int n2, int nt0, int nt1, int32_t *__restrict__ rcnt,
@@ -118,7 +126,7 @@ __global__ void __launch_bounds__(256) tile_sizes_kernel(int64_t ntiles, const i
     const int4 *rm = reinterpret_cast<const int4 *>(rowmap + t * kTV);
     for (int i = 0; i < kTV / 4; ++i) { const int4 v = __ldg(rm + i); rows = rows || v.x >= 0 || v.y >= 0 || v.z >= 0 || v.w >= 0; }
     int nw = 0;
-    if (rows) { nw = (nb + seg_batches - 1) / seg_batches; if (nw < 1) nw = 1; }
+    if (rows) { const int sl = tile_seg_len(nb, seg_batches); nw = (nb + sl - 1) / sl; if (nw < 1) nw = 1; }
     nbatch[t] = rows ? nb : 0;
     nwork[t] = nw;
     if (nw > 1) { atomicAdd(totals, 1); atomicAdd(totals + 1, nw); }
@@ -180,9 +188,10 @@ __global__ void __launch_bounds__(256) tile_work_kernel(int64_t ntiles, const in
     if (nw == 1) { work[w0] = make_int4((int)t, b0, b1, -1); return; }
     const int s0 = atomicAdd(cursors, nw);
     const int at = atomicAdd(cursors + 1, 1);
+    const int sl = tile_seg_len(b1 - b0, seg_batches);
     for (int j = 0; j < nw; ++j) {
-        const int a = b0 + j * seg_batches;
-        work[w0 + j] = make_int4((int)t, a, a + seg_batches < b1 ? a + seg_batches : b1, s0 + j);
+        const int a = b0 + j * sl;
+        work[w0 + j] = make_int4((int)t, a, a + sl < b1 ? a + sl : b1, s0 + j);
     }
     split[at] = make_int4((int)t, s0, nw, 0);
 }
@@ -190,64 +199,96 @@ __global__ void __launch_bounds__(256) tile_work_kernel(int64_t ntiles, const in
 // ---- apply ---------------------------------------------------------------------------------------------
 // Lane geometry: a group of GS = CL * PLN lanes serves one work item.  Lane (cl, pl) holds coils 2cl, 2cl+1
 // of the x-rows (y = pl % 4, z = z0 .. z0 + ZPL-1) of the tile, z0 = (pl / 4) * ZPL, ZPL = 16 / PLN:
-// 4 * ZPL points, two packed accumulators each.
+// 4 * ZPL points, two packed accumulators each.  Few point lanes (PLN = 4: 16 points per lane) amortise the
+// shared-memory reads of an entry over 32 packed multiply-adds: the LSU issues one instruction per 1.8 cycles
+// per SM, and with 16 point lanes it, not the arithmetic, bounds the kernel (ncu, profiles/r02_s6_tiles.md).
+//
+// Everything that comes from global memory arrives through cp.async into a ring of kTRing slots per lane
+// group, a slot = one batch of entries (208 bytes) + the k-space rows of its four samples (4 x 16*CL bytes):
+//   iteration k:  wait until batch k's rows and batch k+2's entries have landed
+//                 issue the gathers of batch k+2 (ids are in its slot)             |  one commit group
+//                 consume batch k from shared memory                               |  per iteration
+//                 re-fill slot k with the entries of batch k+4                     |
+// so no register is held across a global-memory latency and no lane ever waits on one.  The loop count is the
+// maximum over the groups of a warp (idle groups skip the body), which keeps every barrier a full-warp one.
+template <int CL>
+struct TileRing {
+    static constexpr int XB = 16 * CL;                         // bytes of one sample's coils
+    static constexpr int SLOT = kTBatchBytes + kTB * XB;
+    static constexpr int BYTES = kTRing * SLOT + 16;           // +16: consecutive groups start 20 banks apart
+};
+
 template <int CL, int PLN>
 struct TileLanes {
     static constexpr int GS = CL * PLN, GPB = 256 / GS, ZPL = 16 / PLN;
-    int gl, group, coil, y, z0;
-    unsigned gmask;
+    int gl, group, cl, y, z0;
     unsigned char *ring;
     __device__ __forceinline__ TileLanes(unsigned char *ring_all) {
         gl = (int)(threadIdx.x & (GS - 1)); group = (int)(threadIdx.x / GS);
-        coil = 2 * (gl & (CL - 1));
+        cl = gl & (CL - 1);
         const int pl = gl / CL;
         y = pl & 3; z0 = (pl >> 2) * ZPL;
-        gmask = GS >= 32 ? 0xffffffffu : (((1u << GS) - 1u) << (((int)(threadIdx.x & 31) / GS) * GS));
-        ring = ring_all + (size_t)group * (kTRing * kTBatchBytes);
+        ring = ring_all + (size_t)group * TileRing<CL>::BYTES;
     }
 };
 
-__device__ __forceinline__ void tile_issue_batch(unsigned char *slot, const unsigned char *src, int gl, int GS) {
-    for (int c = gl; c < kTBatchBytes / 16; c += GS) {
-        const unsigned d = (unsigned)__cvta_generic_to_shared(slot + 16 * c);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src + 16 * c) : "memory");
+__device__ __forceinline__ void tile_cp16(unsigned char *dst, const void *src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
+}
+
+template <int GS>
+__device__ __forceinline__ void tile_issue_stream(unsigned char *slot, const unsigned char *src, int gl) {
+#pragma unroll
+    for (int c0 = 0; c0 < kTBatchBytes / 16; c0 += GS) {
+        const int c = c0 + gl;
+        if (c < kTBatchBytes / 16) tile_cp16(slot + 16 * c, src + 16 * c);
     }
 }
 
-// acc[q][j][0..1] += sum over the entries of batches [b0, b1) of wz[z0+q] * wy[y] * wx[j] * X[id]
-template <int ZPL>
-__device__ __forceinline__ void tile_walk(int b0, int b1, const unsigned char *__restrict__ ent, const char *xb,
-                                          uint32_t xpitch_bytes, pk2 (&acc)[ZPL][kTE][2], unsigned char *ring, int gl,
-                                          int GS, int y, int z0, unsigned gmask) {
-    const int nb = b1 - b0;
-    const unsigned char *src = ent + (int64_t)b0 * kTBatchBytes;
+// k-space rows of the four samples of the batch in `slot` (its ids have landed): 16 bytes per lane
+template <int CL, int GS>
+__device__ __forceinline__ void tile_issue_gather(unsigned char *slot, const char *xb, uint32_t xpitch_bytes, int C, int gl) {
 #pragma unroll
-    for (int k = 0; k < kTRing; ++k) {
-        if (k < nb) tile_issue_batch(ring + k * kTBatchBytes, src + (int64_t)k * kTBatchBytes, gl, GS);
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    for (int c0 = 0; c0 < kTB * CL; c0 += GS) {
+        const int c = c0 + gl;
+        const int u = c / CL, part = c % CL;
+        if (c < kTB * CL && 2 * part < C) {
+            const uint32_t id = reinterpret_cast<const uint32_t *>(slot)[u];
+            tile_cp16(slot + kTBatchBytes + u * (16 * CL) + 16 * part, xb + (uint64_t)id * xpitch_bytes + 16 * part);
+        }
     }
-    int slot = 0;
-    for (int k = 0; k < nb; ++k) {
-        asm volatile("cp.async.wait_group %0;\n" ::"n"(kTRing - 1) : "memory");
-        __syncwarp(gmask);
-        const unsigned char *sl = ring + slot * kTBatchBytes;
-        const int4 id = *reinterpret_cast<const int4 *>(sl);
-        const int idv[kTB] = {id.x, id.y, id.z, id.w};
-        float4 x[kTB];
+}
+
+template <int CL, int ZPL>
+__device__ __forceinline__ void tile_consume(const unsigned char *sl, int cl, int y, int z0, pk2 (&acc)[ZPL][kTE][2]) {
 #pragma unroll
-        for (int u = 0; u < kTB; ++u)
-            x[u] = __ldg(reinterpret_cast<const float4 *>(xb + (uint64_t)(uint32_t)idv[u] * xpitch_bytes));
+    for (int u = 0; u < kTB; ++u) {
+        const float4 wx = *reinterpret_cast<const float4 *>(sl + 16 + 16 * u);
+        const float wy = *reinterpret_cast<const float *>(sl + 16 + 16 * kTB + 16 * u + 4 * y);
+        float wz[ZPL];
+        const unsigned char *zp = sl + 16 + 32 * kTB + 16 * u + 4 * z0;
+        if (ZPL == 4) { const float4 v = *reinterpret_cast<const float4 *>(zp); wz[0] = v.x; wz[1 % ZPL] = v.y; wz[2 % ZPL] = v.z; wz[3 % ZPL] = v.w; }
+        else if (ZPL == 2) { const float2 v = *reinterpret_cast<const float2 *>(zp); wz[0] = v.x; wz[1 % ZPL] = v.y; }
+        else wz[0] = *reinterpret_cast<const float *>(zp);
+        const float4 xv = *reinterpret_cast<const float4 *>(sl + kTBatchBytes + u * (16 * CL) + 16 * cl);
+        const float wxv[kTE] = {wx.x, wx.y, wx.z, wx.w};
+        const pk2 x0 = p_make(xv.x, xv.y), x1 = p_make(xv.z, xv.w);
+        if (ZPL >= 4) {
+            // 16 points per lane: scale the sample by the four x weights once, then one multiply-add per point
+            pk2 t0[kTE], t1[kTE];
 #pragma unroll
-        for (int u = 0; u < kTB; ++u) {
-            const float4 wx = *reinterpret_cast<const float4 *>(sl + 16 + 16 * u);
-            const float wy = *reinterpret_cast<const float *>(sl + 16 + 16 * kTB + 16 * u + 4 * y);
-            float wz[ZPL];
-            const unsigned char *zp = sl + 16 + 32 * kTB + 16 * u + 4 * z0;
-            if (ZPL == 4) { const float4 v = *reinterpret_cast<const float4 *>(zp); wz[0] = v.x; wz[1 % ZPL] = v.y; wz[2 % ZPL] = v.z; wz[3 % ZPL] = v.w; }
-            else if (ZPL == 2) { const float2 v = *reinterpret_cast<const float2 *>(zp); wz[0] = v.x; wz[1 % ZPL] = v.y; }
-            else wz[0] = *reinterpret_cast<const float *>(zp);
-            const float wxv[kTE] = {wx.x, wx.y, wx.z, wx.w};
-            const pk2 x0 = p_make(x[u].x, x[u].y), x1 = p_make(x[u].z, x[u].w);
+            for (int j = 0; j < kTE; ++j) { t0[j] = p_scale(wxv[j], x0); t1[j] = p_scale(wxv[j], x1); }
+#pragma unroll
+            for (int q = 0; q < ZPL; ++q) {
+                const float wzy = wz[q] * wy;
+#pragma unroll
+                for (int j = 0; j < kTE; ++j) {
+                    acc[q][j][0] = p_fma(p_bc(wzy), t0[j], acc[q][j][0]);
+                    acc[q][j][1] = p_fma(p_bc(wzy), t1[j], acc[q][j][1]);
+                }
+            }
+        } else {
 #pragma unroll
             for (int q = 0; q < ZPL; ++q) {
                 const float wzy = wz[q] * wy;
@@ -259,12 +300,43 @@ __device__ __forceinline__ void tile_walk(int b0, int b1, const unsigned char *_
                 }
             }
         }
-        __syncwarp(gmask);                                           // every lane has read the slot
-        if (k + kTRing < nb) tile_issue_batch(ring + slot * kTBatchBytes, src + (int64_t)(k + kTRing) * kTBatchBytes, gl, GS);
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
-        if (++slot == kTRing) slot = 0;
     }
 }
+
+// acc[q][j][0..1] += sum over the entries of batches [b0, b0 + nb) of wz[z0+q] * wy[y] * wx[j] * X[id]; nbmax = the
+// largest nb among the groups of this warp
+template <int CL, int PLN>
+__device__ __forceinline__ void tile_walk(int b0, int nb, int nbmax, const unsigned char *__restrict__ ent, const char *xb,
+                                          uint32_t xpitch_bytes, int C, pk2 (&acc)[16 / PLN][kTE][2],
+                                          const TileLanes<CL, PLN> &ln) {
+    constexpr int GS = CL * PLN, SLOT = TileRing<CL>::SLOT;
+    const unsigned char *src = ent + (int64_t)b0 * kTBatchBytes;
+    unsigned char *ring = ln.ring;
+#pragma unroll
+    for (int k = 0; k < kTRing; ++k)
+        if (k < nb) tile_issue_stream<GS>(ring + k * SLOT, src + (int64_t)k * kTBatchBytes, ln.gl);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncwarp();
+    if (0 < nb) tile_issue_gather<CL, GS>(ring, xb, xpitch_bytes, C, ln.gl);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    if (1 < nb) tile_issue_gather<CL, GS>(ring + SLOT, xb, xpitch_bytes, C, ln.gl);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    int slot = 0;
+    for (int k = 0; k < nbmax; ++k) {
+        asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        __syncwarp();
+        unsigned char *sl = ring + slot * SLOT;
+        if (k + 2 < nb) tile_issue_gather<CL, GS>(ring + ((slot + 2) & (kTRing - 1)) * SLOT, xb, xpitch_bytes, C, ln.gl);
+        if (k < nb) tile_consume<CL, 16 / PLN>(sl, ln.cl, ln.y, ln.z0, acc);
+        __syncwarp();                                                // every lane has read the slot
+        if (k + kTRing < nb) tile_issue_stream<GS>(sl, src + (int64_t)(k + kTRing) * kTBatchBytes, ln.gl);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        slot = (slot + 1) & (kTRing - 1);
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+static_assert((kTRing & (kTRing - 1)) == 0, "ring depth must be a power of two");
 
 template <int ZPL>
 __device__ __forceinline__ void tile_store(const pk2 (&acc)[ZPL][kTE][2], c64 alpha, int tile, int y, int z0,
@@ -288,6 +360,7 @@ __device__ __forceinline__ void tile_store(const pk2 (&acc)[ZPL][kTE][2], c64 al
 
 // Yil[rowmap[64*tile + p]][c] = alpha * sum_e wz_e[pz] wy_e[py] wx_e[px] * Xil[id_e][c]   (items with slot < 0)
 // scratch[slot][p][c]         =         the same sum over the item's batches                  (items of split tiles)
+// for the C <= 2*CL columns starting at Xil / Yil / scratch (the host loops over chunks of 16 columns)
 template <int CL, int PLN>
 __global__ void __launch_bounds__(256) kb_tiles_kernel(int nwork, int C, c64 alpha, const int4 *__restrict__ work,
                                                        const unsigned char *__restrict__ ent, const c64 *__restrict__ Xil,
@@ -298,59 +371,88 @@ __global__ void __launch_bounds__(256) kb_tiles_kernel(int nwork, int C, c64 alp
     extern __shared__ __align__(16) unsigned char tile_ring[];
     const L ln(tile_ring);
     const int idx = blockIdx.x * L::GPB + ln.group;
-    if (idx >= nwork) return;
-    const int4 d = __ldg(work + idx);
-    const bool coil_ok = ln.coil < C;
-    const char *xb = reinterpret_cast<const char *>(Xil + (coil_ok ? ln.coil : 0));
+    const bool live = idx < nwork;
+    int4 d = make_int4(0, 0, 0, -1);
+    if (live) d = __ldg(work + idx);
+    const int nb = d.z - d.y;
+    const int nbmax = __reduce_max_sync(0xffffffffu, nb);
+    const int coil = 2 * ln.cl;
     pk2 acc[L::ZPL][kTE][2];
 #pragma unroll
     for (int q = 0; q < L::ZPL; ++q)
 #pragma unroll
         for (int j = 0; j < kTE; ++j) { acc[q][j][0] = p_make(0.f, 0.f); acc[q][j][1] = p_make(0.f, 0.f); }
-    if (d.y < d.z) tile_walk<L::ZPL>(d.y, d.z, ent, xb, xpitch_bytes, acc, ln.ring, ln.gl, L::GS, ln.y, ln.z0, ln.gmask);
-    if (!coil_ok) return;
+    tile_walk<CL, PLN>(d.y, nb, nbmax, ent, reinterpret_cast<const char *>(Xil), xpitch_bytes, C, acc, ln);
+    if (!live || coil >= C) return;
     if (d.w < 0) {
-        tile_store<L::ZPL>(acc, alpha, d.x, ln.y, ln.z0, rowmap, Yil, ypitch, ln.coil);
+        tile_store<L::ZPL>(acc, alpha, d.x, ln.y, ln.z0, rowmap, Yil, ypitch, coil);
     } else {
 #pragma unroll
         for (int q = 0; q < L::ZPL; ++q)
 #pragma unroll
             for (int j = 0; j < kTE; ++j) {
                 const int p = ((ln.z0 + q) * kTE + ln.y) * kTE + j;
-                *reinterpret_cast<float4 *>(scratch + ((int64_t)d.w * kTV + p) * cpitch + ln.coil) =
+                *reinterpret_cast<float4 *>(scratch + ((int64_t)d.w * kTV + p) * cpitch + coil) =
                     make_float4(p_lo(acc[q][j][0]), p_hi(acc[q][j][0]), p_lo(acc[q][j][1]), p_hi(acc[q][j][1]));
             }
     }
 }
 
-// split tiles: partial sums added in segment order
-template <int CL, int PLN>
+// split tiles: one CTA per tile; thread (sl, point, coil lane) adds the partial sums of segments sl, sl + NS, ...
+// (four independent chains for memory-level parallelism), the NS segment lanes are then added in order through
+// shared memory: a fixed summation tree, independent of scheduling.  With 8 coil lanes (16 columns) the 512
+// (point, coil lane) pairs of a tile take two rounds of the 256 threads.
+template <int CL>
 __global__ void __launch_bounds__(256) kb_tiles_fold_kernel(int nsplit, int C, c64 alpha, const int4 *__restrict__ split,
                                                             const c64 *__restrict__ scratch, int cpitch,
                                                             c64 *__restrict__ Yil, int64_t ypitch,
                                                             const int32_t *__restrict__ rowmap) {
-    typedef TileLanes<CL, PLN> L;
-    const L ln(nullptr);
-    const int idx = blockIdx.x * L::GPB + ln.group;
-    if (idx >= nsplit || ln.coil >= C) return;
-    const int4 d = __ldg(split + idx);
-    pk2 acc[L::ZPL][kTE][2];
+    constexpr int PAIRS = kTV * CL;
+    constexpr int NS = PAIRS >= 256 ? 1 : 256 / PAIRS, ROUNDS = PAIRS > 256 ? PAIRS / 256 : 1;
+    __shared__ float4 part[NS > 1 ? (NS - 1) * PAIRS : 1];
+    const int4 d = __ldg(split + blockIdx.x);
+    const int64_t seg_stride = (int64_t)kTV * cpitch;
 #pragma unroll
-    for (int q = 0; q < L::ZPL; ++q)
+    for (int rd = 0; rd < ROUNDS; ++rd) {
+        const int item = (int)threadIdx.x % (PAIRS < 256 ? PAIRS : 256) + 256 * rd;
+        const int sl = PAIRS < 256 ? (int)threadIdx.x / PAIRS : 0;
+        const int cl = item % CL, p = item / CL;
+        const int coil = 2 * cl;
+        pk2 a0[4], a1[4];
 #pragma unroll
-        for (int j = 0; j < kTE; ++j) { acc[q][j][0] = p_make(0.f, 0.f); acc[q][j][1] = p_make(0.f, 0.f); }
-    for (int sgm = d.y; sgm < d.y + d.z; ++sgm) {
+        for (int u = 0; u < 4; ++u) { a0[u] = p_make(0.f, 0.f); a1[u] = p_make(0.f, 0.f); }
+        const c64 *base = scratch + ((int64_t)d.y * kTV + p) * cpitch + coil;
+        for (int g = sl; g < d.z; g += 4 * NS) {
 #pragma unroll
-        for (int q = 0; q < L::ZPL; ++q)
-#pragma unroll
-            for (int j = 0; j < kTE; ++j) {
-                const int p = ((ln.z0 + q) * kTE + ln.y) * kTE + j;
-                const float4 v = *reinterpret_cast<const float4 *>(scratch + ((int64_t)sgm * kTV + p) * cpitch + ln.coil);
-                acc[q][j][0] = p_add(acc[q][j][0], p_make(v.x, v.y));
-                acc[q][j][1] = p_add(acc[q][j][1], p_make(v.z, v.w));
+            for (int u = 0; u < 4; ++u) {
+                const int sg = g + u * NS;
+                if (sg < d.z) {
+                    const float4 v = __ldcs(reinterpret_cast<const float4 *>(base + sg * seg_stride));
+                    a0[u] = p_add(a0[u], p_make(v.x, v.y));
+                    a1[u] = p_add(a1[u], p_make(v.z, v.w));
+                }
             }
+        }
+        pk2 s0 = p_add(p_add(a0[0], a0[1]), p_add(a0[2], a0[3])), s1 = p_add(p_add(a1[0], a1[1]), p_add(a1[2], a1[3]));
+        if (NS > 1) {
+            if (sl > 0) part[(sl - 1) * PAIRS + item] = make_float4(p_lo(s0), p_hi(s0), p_lo(s1), p_hi(s1));
+            __syncthreads();
+            if (sl == 0) {
+#pragma unroll
+                for (int q = 1; q < NS; ++q) {
+                    const float4 v = part[(q - 1) * PAIRS + item];
+                    s0 = p_add(s0, p_make(v.x, v.y)); s1 = p_add(s1, p_make(v.z, v.w));
+                }
+            }
+        }
+        if (sl == 0 && coil < C) {
+            const int64_t out = (int64_t)__ldg(rowmap + (int64_t)d.x * kTV + p);
+            if (out >= 0) {
+                const c64 o0 = cmul(alpha, mk(p_lo(s0), p_hi(s0))), o1 = cmul(alpha, mk(p_lo(s1), p_hi(s1)));
+                __stcs(reinterpret_cast<float4 *>(Yil + out * ypitch + coil), make_float4(o0.x, o0.y, o1.x, o1.y));
+            }
+        }
     }
-    tile_store<L::ZPL>(acc, alpha, d.x, ln.y, ln.z0, rowmap, Yil, ypitch, ln.coil);
 }
 
 static int tiles_pow2_ceil(int64_t v) { int p = 1; while (p < v) p <<= 1; return p; }
@@ -491,7 +593,7 @@ int ib200_kb_tiles_apply(void *stream, int64_t ncols, float ar, float ai, int nw
     IB200_RANGE("ib200_kb_tiles_apply");
     IB200_REQUIRE(nwork >= 0 && nsplit >= 0 && ncols >= 0, "bad arguments");
     if (nwork == 0 || ncols == 0) return 0;
-    IB200_REQUIRE(ncols <= 8 && ncols % 2 == 0, "tile gather serves 2, 4, 6 or 8 columns");
+    IB200_REQUIRE(ncols <= 64 && ncols % 2 == 0, "tile gather serves an even number of at most 64 columns");
     IB200_REQUIRE(work && entries && Xil && Yil && rowmap, "null pointer");
     IB200_REQUIRE(xpitch >= ncols && ypitch >= ncols && xpitch % 2 == 0 && ypitch % 2 == 0, "bad pitch");
     IB200_REQUIRE(((uintptr_t)Xil & 15) == 0 && ((uintptr_t)Yil & 15) == 0 && ((uintptr_t)entries & 15) == 0,
@@ -500,39 +602,46 @@ int ib200_kb_tiles_apply(void *stream, int64_t ncols, float ar, float ai, int nw
     IB200_REQUIRE(nsplit == 0 || (split && scratch && ((uintptr_t)scratch & 15) == 0), "split arrays missing");
     const c64 alpha = mk(ar, ai);
     cudaStream_t s = as_stream(stream);
-    const int CL = tiles_pow2_ceil(ncols / 2);
-    int PLN = CL == 4 ? 8 : (lanes == 4 || lanes == 8 || lanes == 16 ? lanes : 8);   // point lanes per item
+    int want = lanes == 4 || lanes == 8 || lanes == 16 ? lanes : 4;  // point lanes per item
     if (const char *e = getenv("IB200_TILES_PLN")) {                 // tuning knob (tools/)
         const int v = atoi(e);
-        if ((v == 4 || v == 8 || v == 16) && CL * v <= 32) PLN = v;
+        if (v == 4 || v == 8 || v == 16) want = v;
     }
-    if (CL * PLN > 32) PLN = 32 / CL;
-    const int GS = CL * PLN, GPB = 256 / GS;
-    const int cpitch = 2 * CL;
-    const size_t ring_bytes = (size_t)GPB * kTRing * kTBatchBytes;
     const uint32_t pb = (uint32_t)(xpitch * sizeof(c64));
+    // chunks of at most 16 columns: 8 coil lanes x 4 point lanes fill a warp
+    for (int64_t c0 = 0; c0 < ncols; c0 += 16) {
+        const int cc = (int)(ncols - c0 < 16 ? ncols - c0 : 16);
+        const int CL = tiles_pow2_ceil(cc / 2);
+        int PLN = want;
+        while (CL * PLN > 32) PLN /= 2;
+        const int GS = CL * PLN, GPB = 256 / GS;
+        const int cpitch = 2 * CL;
+        const c64 *X = (const c64 *)Xil + c0;
+        c64 *Y = (c64 *)Yil + c0;
 #define IB200_TILES_CASE(cl, pln)                                                                                      \
-    case (cl) * 32 + (pln):                                                                                            \
+    case (cl) * 32 + (pln): {                                                                                          \
+        const size_t ring_bytes = (size_t)GPB * TileRing<cl>::BYTES;                                                   \
         if (ring_bytes > 48 * 1024)                                                                                    \
             IB200_TRY(cudaFuncSetAttribute(kb_tiles_kernel<cl, pln>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes)); \
-        kb_tiles_kernel<cl, pln><<<(unsigned)ceil_div(nwork, GPB), 256, ring_bytes, s>>>(nwork, (int)ncols, alpha, (const int4 *)work, \
-                                                                (const unsigned char *)entries, (const c64 *)Xil, pb,  \
-                                                                (c64 *)Yil, ypitch, rowmap, (c64 *)scratch, cpitch);   \
+        kb_tiles_kernel<cl, pln><<<(unsigned)ceil_div(nwork, GPB), 256, ring_bytes, s>>>(nwork, cc, alpha, (const int4 *)work, \
+                                                                (const unsigned char *)entries, X, pb, Y, ypitch, rowmap, \
+                                                                (c64 *)scratch, cpitch);                               \
         if (nsplit > 0) {                                                                                              \
             count_launch();                                                                                            \
-            kb_tiles_fold_kernel<cl, pln><<<(unsigned)ceil_div(nsplit, GPB), 256, 0, s>>>(nsplit, (int)ncols, alpha,   \
-                                                                (const int4 *)split, (const c64 *)scratch, cpitch,     \
-                                                                (c64 *)Yil, ypitch, rowmap);                           \
+            kb_tiles_fold_kernel<cl><<<(unsigned)nsplit, 256, 0, s>>>(nsplit, cc, alpha, (const int4 *)split,          \
+                                                                      (const c64 *)scratch, cpitch, Y, ypitch, rowmap); \
         }                                                                                                              \
-        break
-    switch (CL * 32 + PLN) {
-        IB200_TILES_CASE(1, 4); IB200_TILES_CASE(1, 8); IB200_TILES_CASE(1, 16);
-        IB200_TILES_CASE(2, 4); IB200_TILES_CASE(2, 8); IB200_TILES_CASE(2, 16);
-        IB200_TILES_CASE(4, 4); IB200_TILES_CASE(4, 8);
-        default: set_error("internal: no tile gather for CL=%d PLN=%d", CL, PLN); return IB200_E_UNSUPPORTED;
-    }
+    } break
+        switch (CL * 32 + PLN) {
+            IB200_TILES_CASE(1, 4); IB200_TILES_CASE(1, 8); IB200_TILES_CASE(1, 16);
+            IB200_TILES_CASE(2, 4); IB200_TILES_CASE(2, 8); IB200_TILES_CASE(2, 16);
+            IB200_TILES_CASE(4, 4); IB200_TILES_CASE(4, 8);
+            IB200_TILES_CASE(8, 4);
+            default: set_error("internal: no tile gather for CL=%d PLN=%d", CL, PLN); return IB200_E_UNSUPPORTED;
+        }
 #undef IB200_TILES_CASE
-    IB200_LAUNCH_CHECK();
+        IB200_LAUNCH_CHECK();
+    }
     return 0;
 }
 

@@ -238,7 +238,7 @@ class SenseDevice(object):
 
     def _want_tiles(self):
         return bool(self.allow_tiles and self.allow_separable and self.C % 2 == 0 and self.C <= self.tiles_max_coils
-                    and self.C <= 8 and tuple(self.tile) == (4, 4, 4))
+                    and tuple(self.tile) == (4, 4, 4))
 
     def __del__(self):
         try:

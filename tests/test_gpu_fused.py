@@ -116,15 +116,14 @@ def test_fused_long_rows(B, C, runs, monkeypatch):
 @pytest.mark.parametrize("lanes", [0, 4, 8, 16])
 @pytest.mark.parametrize("segb", [64, 2], ids=["whole-tiles", "split-tiles"])
 @pytest.mark.parametrize("N,C,traj,weighted", [((16, 16, 16), 2, "koosh", False), ((16, 26, 16), 4, "random", True),
-                                               ((26, 16, 16), 6, "koosh", True), ((16, 16, 26), 8, "koosh", False)])
+                                               ((26, 16, 16), 6, "koosh", True), ((16, 16, 26), 8, "koosh", False),
+                                               ((16, 16, 16), 16, "koosh", True), ((16, 16, 16), 20, "koosh", False)])
 def test_fused_tile_blocks(B, N, C, traj, weighted, segb, lanes, monkeypatch):
     """Adjoint gridding on tile-block entries (csrc/kbtiles.cu, the few-coil formulation of coil-sharded operators):
     every lane geometry, whole tiles and tiles cut into work items with the ordered fold (segment length forced
     low so that the dense k-space centre of a small kooshball splits), with and without support windows."""
     from indigo_b200 import fused
-    if lanes == 16 and C > 4:
-        pytest.skip("16 point lanes x 4 coil lanes exceed a warp")
-    monkeypatch.setattr(fused.SenseDevice, "tiles_max_coils", 8)
+    monkeypatch.setattr(fused.SenseDevice, "tiles_max_coils", 32)
     monkeypatch.setattr(fused.SenseDevice, "tiles_seg_batches", segb)
     monkeypatch.setattr(fused.SenseDevice, "tiles_lanes", lanes)
     monkeypatch.setattr(fused.SenseDevice, "window_min_saving", 0.0)
