@@ -156,7 +156,7 @@ def fused_kernel_bytes(dev):
         "fft_pass[z fwd]": (8 * C * (py + inside), third, "fftn/3"),
         "kb_gather": (8 * C * inside + 96 * M + 8 * C * M, ccs_G, "ccsrmm(G')"),
         "csrmm_runs": (ent + 8 * C * M + 8 * C * inside, ccs_GH, "ccsrmm(G',adj)"),
-        "kb_tiles": (tent + 8 * C * M + 8 * C * inside, ccs_GH, "ccsrmm(G',adj)"),
+        "kb_blocks": (tent + 8 * C * M + 8 * C * inside, ccs_GH, "ccsrmm(G',adj)"),
         "fft_pass[z inv]": (8 * C * (inside + py), third, "ifftn/3"),
         "fft_pass[y inv]": (8 * C * (py + px), third, "ifftn/3"),
         "sense_combine_pk[x]": (8 * C * px + 8 * nvox * C + 8 * nvox, ccs_PH + third, "ifftn/3 + ccsrmm(P^H)"),

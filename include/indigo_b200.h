@@ -202,32 +202,33 @@ int ib200_ccsrmm_runs(void *stream, int64_t kp, int64_t ncols, float alpha_re, f
                       const int32_t *ids, const void *w4, const void *Xil, int64_t xpitch, void *Yil, int64_t ypitch,
                       const int32_t *rowmap, int seg_len, const int32_t *seg_desc, int nseg, const int32_t *split_desc,
                       int nsplit, void *scratch);
-/* Tile-block form of the adjoint gridding for operators with few coils (coil-sharded SENSE operators,
- * csrc/kbtiles.cu; replaces ccsrmm(G', adjoint), indigo/backends/backend.py:560-596, for the matrix that
- * indigo/interp.py:19-80 emits).  Built from the separable records of ib200_kb_records, no stored matrix:
- * one entry (sample, wx[4], wy[4], wz[4]) per (sample, 4x4x4 grid tile) pair, entries of a tile consecutive,
- * ordered by record, in batches of four (ib200_kb_tiles_batch_bytes() bytes each, zero-weight padding).
- * Tiles are numbered and their points ordered as by ib200_grid_tile_rank with tile 4x4x4; rowmap[64*tile + p]
- * is the output row of point p (< 0: nothing stored).  A tile with more than seg_batches batches is cut into
- * several work items whose partial sums are added in order by a second kernel.
- *   ib200_kb_tiles_count: fills bptr[tiles+1] (first batch of every tile) and wptr[tiles+1] (first work item);
- *     host_totals[5] = {tiles, batches, work items, split tiles, work items of split tiles}.  Tiles without a
- *     row inside rowmap get nothing; tiles with rows but without samples get one empty work item (they are
+/* Block form of the adjoint gridding (csrc/kbblocks.cu; replaces ccsrmm(G', adjoint),
+ * indigo/backends/backend.py:560-596, for the matrix that indigo/interp.py:19-80 emits).  Built from the
+ * separable records of ib200_kb_records, no stored matrix: the grid is cut into blocks of 4 x by x bz points
+ * ((by, bz) = (4,4), (2,2), (2,1) or (1,1), inside the 4x4x4 tiles of ib200_grid_tile_rank) and every (sample,
+ * block) pair that meets is one entry (sample, wx[4], wy[by], wz[bz]); entries of a block are consecutive,
+ * ordered by record, in batches of four (ib200_kb_blocks_batch_bytes(by, bz) bytes each, zero-weight padding).
+ * rowmap[64*tile + (z*4 + y)*4 + x] is the output row of a point (< 0: nothing stored).  A block with more than
+ * seg_batches batches is cut into several work items whose partial sums are added in a fixed order by a second
+ * kernel.
+ *   ib200_kb_blocks_count: fills bptr[blocks+1] (first batch of every block) and wptr[blocks+1] (first work item);
+ *     host_totals[5] = {blocks, batches, work items, split blocks, work items of split blocks}.  Blocks without
+ *     a row inside rowmap get nothing; blocks with rows but without samples get one empty work item (they are
  *     overwritten with zeros on every apply).
- *   ib200_kb_tiles_fill: writes entries[batches * batch_bytes], work[4 * work items], split[4 * split tiles].
- *   ib200_kb_tiles_apply: Yil[rowmap[64*t + p]][c] = alpha * sum_e wz_e[pz] wy_e[py] wx_e[px] * Xil[out(e)][c]
- *     for an even number of at most 64 interleaved columns (served in chunks of 16); scratch: (work items of
- *     split tiles) * 64 * 2*pow2ceil(min(ncols,16)/2) complex words; lanes: 0 or the number of lanes (4, 8, 16)
- *     that share the points of a tile.
+ *   ib200_kb_blocks_fill: writes entries[batches * batch_bytes], work[4 * work items], split[4 * split blocks].
+ *   ib200_kb_blocks_apply: Yil[rowmap[point]][c] = alpha * sum_e wz_e wy_e wx_e * Xil[out(e)][c] for an even
+ *     number of at most 64 interleaved columns (served in chunks of 16); scratch: (work items of split blocks) *
+ *     4*by*bz * 2*pow2ceil(min(ncols,16)/2) complex words; lanes: 0 or the number of lanes (1, 2, 4, 8, 16) that
+ *     share the rows of a block.
  * The first two synchronise. */
-int ib200_kb_tiles_batch_bytes(void);
-int ib200_kb_tiles_count(void *stream, int64_t m, const void *records, const int64_t grid[3], const int32_t *rowmap,
-                         int seg_batches, int32_t *bptr, int32_t *wptr, int64_t *host_totals);
-int ib200_kb_tiles_fill(void *stream, int64_t m, const void *records, const int64_t grid[3], int seg_batches,
-                        const int32_t *bptr, const int32_t *wptr, void *entries, int32_t *work, int32_t *split);
-int ib200_kb_tiles_apply(void *stream, int64_t ncols, float alpha_re, float alpha_im, int nwork, const int32_t *work,
-                         const void *entries, const void *Xil, int64_t xpitch, void *Yil, int64_t ypitch,
-                         const int32_t *rowmap, int nsplit, const int32_t *split, void *scratch, int lanes);
+int ib200_kb_blocks_batch_bytes(int by, int bz);
+int ib200_kb_blocks_count(void *stream, int64_t m, const void *records, const int64_t grid[3], int by, int bz,
+                          const int32_t *rowmap, int seg_batches, int32_t *bptr, int32_t *wptr, int64_t *host_totals);
+int ib200_kb_blocks_fill(void *stream, int64_t m, const void *records, const int64_t grid[3], int by, int bz, int seg_batches,
+                         const int32_t *bptr, const int32_t *wptr, void *entries, int32_t *work, int32_t *split);
+int ib200_kb_blocks_apply(void *stream, int64_t ncols, int by, int bz, float alpha_re, float alpha_im, int nwork,
+                          const int32_t *work, const void *entries, const void *Xil, int64_t xpitch, void *Yil,
+                          int64_t ypitch, const int32_t *rowmap, int nsplit, const int32_t *split, void *scratch, int lanes);
 /* k-space support windows of a trajectory (fused SENSE recipe only).  Given the stored adjoint of the
  * gridding matrix in tile-major row order (rowptr[kp+1], rowmap[kp] from ib200_grid_tile_rank) the
  * grid columns are grouped into blocks of block[0] x block[1] points; for each block the hull [lo, hi)

@@ -55,10 +55,10 @@ SIGNATURES = {
     "ib200_csr_runs_count": (_i, [_vp, _i64, _vp, _vp, _i, _vp, POINTER(_i64), POINTER(_i), POINTER(_i)]),
     "ib200_csr_runs_fill": (_i, [_vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ib200_ccsrmm_runs": (_i, [_vp, _i64, _i64, _f, _f, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i, _vp, _i, _vp, _i, _vp]),
-    "ib200_kb_tiles_batch_bytes": (_i, []),
-    "ib200_kb_tiles_count": (_i, [_vp, _i64, _vp, POINTER(_i64), _vp, _i, _vp, _vp, POINTER(_i64)]),
-    "ib200_kb_tiles_fill": (_i, [_vp, _i64, _vp, POINTER(_i64), _i, _vp, _vp, _vp, _vp, _vp]),
-    "ib200_kb_tiles_apply": (_i, [_vp, _i64, _f, _f, _i, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i, _vp, _vp, _i]),
+    "ib200_kb_blocks_batch_bytes": (_i, [_i, _i]),
+    "ib200_kb_blocks_count": (_i, [_vp, _i64, _vp, POINTER(_i64), _i, _i, _vp, _i, _vp, _vp, POINTER(_i64)]),
+    "ib200_kb_blocks_fill": (_i, [_vp, _i64, _vp, POINTER(_i64), _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "ib200_kb_blocks_apply": (_i, [_vp, _i64, _i, _i, _f, _f, _i, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i, _vp, _vp, _i]),
     "ib200_grid_tile_rank2": (_i, [_vp, POINTER(_i64), POINTER(_i64), POINTER(_i64), _vp, POINTER(_i64)]),
     "ib200_grid_tile_rank": (_i, [_vp, POINTER(_i64), POINTER(_i64), _vp, _vp, POINTER(_i64)]),
     "ib200_csr_inspect": (_i, [_vp, _i64, _i64, _vp, _vp, _vp, POINTER(_i64)]),
@@ -88,7 +88,7 @@ SIGNATURES = {
 
 # entry points that return something other than a status code
 _NO_STATUS = {"ib200_last_error", "ib200_version", "ib200_launch_count", "ib200_launch_count_reset",
-              "ib200_fft_plan_describe", "ib200_kb_record_bytes", "ib200_kb_tiles_batch_bytes"}
+              "ib200_fft_plan_describe", "ib200_kb_record_bytes", "ib200_kb_blocks_batch_bytes"}
 
 
 class Library(object):

@@ -46,10 +46,12 @@ class SenseDevice(object):
     allow_sorted_ksp = True    # keep k-space in tile-sorted sample order between the two gridding steps
     allow_runs = True          # adjoint gridding on merged x-runs of the stored adjoint (csrc/csrmm_runs.cu)
     run_long_thresh = 1024     # runs with more entries than this are cut into segments of this length
-    allow_tiles = True         # adjoint gridding on tile-block entries (csrc/kbtiles.cu) when the coils are few
-    tiles_max_coils = 4        # ... i.e. at most this many (coil-sharded operators; the x-runs win above)
-    tiles_seg_batches = 64     # tiles with more batches (of 4 entries) than this are cut into work items of this length
-    tiles_lanes = 0            # lanes sharing the 64 points of a tile (0: kernel default)
+    allow_tiles = True         # adjoint gridding on block entries built from the separable records (csrc/kbblocks.cu)
+    tiles_max_coils = 4        # whole 4x4x4 tiles up to this many coils (coil-sharded operators) ...
+    blocks_max_coils = 0       # ... 4x2x1 blocks up to this many; the x-runs of the stored adjoint above
+    block_shape = None         # (by, bz) forced for every coil count (tests, tools/)
+    tiles_seg_batches = 64     # blocks with more batches (of 4 entries) than this are cut into work items of this length
+    tiles_lanes = 0            # lanes sharing the rows of a block (0: kernel default)
     allow_windows = True       # k-space support windows: skip the grid outside the trajectory's support
     window_min_saving = 0.05   # ... when at least this fraction of the grid lies outside
 
@@ -62,6 +64,10 @@ class SenseDevice(object):
             self.sample_tile = (int(os.environ["IB200_SAMPLE_TILE"]),) * 3
         if os.environ.get("IB200_TILES_MAXC"):                      # tuning knobs (tools/): tile-block adjoint gather
             self.tiles_max_coils = int(os.environ["IB200_TILES_MAXC"])
+        if os.environ.get("IB200_BLOCKS_MAXC"):
+            self.blocks_max_coils = int(os.environ["IB200_BLOCKS_MAXC"])
+        if os.environ.get("IB200_BLOCKS_SHAPE"):
+            self.block_shape = tuple(int(v) for v in os.environ["IB200_BLOCKS_SHAPE"].split(","))
         if os.environ.get("IB200_TILES_SEG"):
             self.tiles_seg_batches = int(os.environ["IB200_TILES_SEG"])
         if os.environ.get("IB200_RUN_LONG"):                        # tuning knob (tools/): run-length threshold
@@ -145,7 +151,7 @@ class SenseDevice(object):
                 # are then neighbours in memory (the original spoke order scatters them over 0.9 GB at cfg3)
                 self.kb = None
                 use_runs = self.allow_runs and C % 2 == 0 and self.tile[0] == 4 and kp % 4 == 0
-                use_tiles = self._want_tiles()
+                use_tiles = self._want_tiles() is not None
                 self.ksp_sorted = bool(self.allow_separable and (use_runs or use_tiles) and self.allow_sorted_ksp)
                 if self.allow_separable:
                     self.kb = kb_records_device(B, self.oN, coord, beta, weights, width, n, perm=self.g_map,
@@ -186,28 +192,30 @@ class SenseDevice(object):
                         self.win, self.rowmap, self.support_fraction = win, rowmap_w, frac
                     except RuntimeError:
                         pass                                            # geometry without persistent packed z passes
-        # few coils (the shard of a coil-sharded operator): tile-block entries built from the separable records, one
-        # 52-byte entry and one gather per (sample, 4x4x4 tile) pair instead of 6.75 run entries (csrc/kbtiles.cu)
+        # block entries built from the separable records: one entry and one gather per (sample, block of 4 x by x bz
+        # grid points) pair -- whole tiles when the coils are few (the shard of a coil-sharded operator)
         self.tiles = None
-        if self.real and self.kb is not None and self._want_tiles():
+        shape = self._want_tiles()
+        if self.real and self.kb is not None and shape:
+            by, bz = shape
             segb = max(1, int(self.tiles_seg_batches))
-            ntile = kp // 64
-            bptr = B.empty_array((ntile + 1,), i32, name='G.H.tiles.batchptr')
-            wptr = B.empty_array((ntile + 1,), i32, name='G.H.tiles.workptr')
+            nblk = kp // 64 * (4 // by) * (4 // bz)
+            bptr = B.empty_array((nblk + 1,), i32, name='G.H.blocks.batchptr')
+            wptr = B.empty_array((nblk + 1,), i32, name='G.H.blocks.workptr')
             tot = (ctypes.c_int64 * 5)()
-            lib.kb_tiles_count(s, self.M, self.kb.ptr, grid3, self.rowmap.ptr, segb, bptr.ptr, wptr.ptr, tot)
+            lib.kb_blocks_count(s, self.M, self.kb.ptr, grid3, by, bz, self.rowmap.ptr, segb, bptr.ptr, wptr.ptr, tot)
             nbat, nwork, nsplit, nslot = int(tot[1]), int(tot[2]), int(tot[3]), int(tot[4])
-            bb = int(lib.kb_tiles_batch_bytes())
-            ent = B.empty_array((max(nbat, 1) * bb // 16 * 2,), np.dtype('int64'), name='G.H.tiles.entries')
-            work = B.empty_array((4 * max(nwork, 1),), i32, name='G.H.tiles.work')
-            split = B.empty_array((4 * max(nsplit, 1),), i32, name='G.H.tiles.split')
-            lib.kb_tiles_fill(s, self.M, self.kb.ptr, grid3, segb, bptr.ptr, wptr.ptr, ent.ptr, work.ptr, split.ptr)
+            bb = int(lib.kb_blocks_batch_bytes(by, bz))
+            ent = B.empty_array((max(nbat, 1) * bb // 8,), np.dtype('int64'), name='G.H.blocks.entries')
+            work = B.empty_array((4 * max(nwork, 1),), i32, name='G.H.blocks.work')
+            split = B.empty_array((4 * max(nsplit, 1),), i32, name='G.H.blocks.split')
+            lib.kb_blocks_fill(s, self.M, self.kb.ptr, grid3, by, bz, segb, bptr.ptr, wptr.ptr, ent.ptr, work.ptr, split.ptr)
             cl = 1
-            while cl < C // 2:
+            while cl < min(C, 16) // 2:
                 cl *= 2
-            scratch = B.empty_array((max(nslot, 1) * 64 * 2 * cl,), _C64, name='G.H.tiles.partial')
+            scratch = B.empty_array((max(nslot, 1) * 4 * by * bz * 2 * cl,), _C64, name='G.H.blocks.partial')
             self.tiles = dict(ent=ent, work=work, nwork=nwork, split=split, nsplit=nsplit, scratch=scratch,
-                              batches=nbat, bytes=nbat * bb)
+                              batches=nbat, bytes=nbat * bb, shape=(by, bz))
             del bptr, wptr
         # x-run lists of the stored adjoint: one gather of a sample serves the four grid points of a tile row;
         # runs longer than run_long_thresh entries are cut into segments with their own lane groups
@@ -237,8 +245,16 @@ class SenseDevice(object):
         self.ksp = B.empty_array((self.M * C,), _C64, name='ksp[m][c]')
 
     def _want_tiles(self):
-        return bool(self.allow_tiles and self.allow_separable and self.C % 2 == 0 and self.C <= self.tiles_max_coils
-                    and tuple(self.tile) == (4, 4, 4))
+        """Block shape (by, bz) of the matrix-free adjoint gather for this coil count, or None (x-runs / stored rows)."""
+        if not (self.allow_tiles and self.allow_separable and self.C % 2 == 0 and tuple(self.tile) == (4, 4, 4)):
+            return None
+        if self.block_shape:
+            return tuple(self.block_shape)
+        if self.C <= self.tiles_max_coils:
+            return (4, 4)
+        if self.C <= self.blocks_max_coils:
+            return (2, 1)
+        return None
 
     def __del__(self):
         try:
@@ -271,7 +287,7 @@ class SenseDevice(object):
             self._grid_to_samples(alpha)
 
     def samples_to_grid(self):
-        with self._step("kb_tiles" if self.tiles is not None else "csrmm_runs"):
+        with self._step("kb_blocks" if self.tiles is not None else "csrmm_runs"):
             self._samples_to_grid()
 
     def _grid_to_samples(self, alpha=1.0):
@@ -292,9 +308,9 @@ class SenseDevice(object):
         lr = self.longrows.ptr if self.nlong else None
         if self.real and self.tiles is not None:
             t = self.tiles
-            lib.kb_tiles_apply(s, self.C, 1.0, 0.0, t['nwork'], t['work'].ptr, t['ent'].ptr, self.ksp.ptr, self.C,
-                               self.grid.ptr, self.C, self.rowmap.ptr, t['nsplit'], t['split'].ptr, t['scratch'].ptr,
-                               int(self.tiles_lanes))
+            lib.kb_blocks_apply(s, self.C, t['shape'][0], t['shape'][1], 1.0, 0.0, t['nwork'], t['work'].ptr, t['ent'].ptr,
+                                self.ksp.ptr, self.C, self.grid.ptr, self.C, self.rowmap.ptr, t['nsplit'], t['split'].ptr,
+                                t['scratch'].ptr, int(self.tiles_lanes))
         elif self.real and self.runs is not None:
             r = self.runs
             lib.ccsrmm_runs(s, self.kp, self.C, 1.0, 0.0, r['ptr'].ptr, r['ids'].ptr, r['w4'].ptr, self.ksp.ptr, self.C,

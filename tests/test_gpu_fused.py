@@ -113,24 +113,25 @@ def test_fused_long_rows(B, C, runs, monkeypatch):
     assert relerr(normal_operator(A) * x, ref.normal(x)) < TOL
 
 
-@pytest.mark.parametrize("lanes", [0, 4, 8, 16])
-@pytest.mark.parametrize("segb", [64, 2], ids=["whole-tiles", "split-tiles"])
+@pytest.mark.parametrize("shape,lanes", [((4, 4), 0), ((4, 4), 4), ((2, 2), 0), ((2, 2), 2), ((2, 1), 0), ((2, 1), 2),
+                                         ((1, 1), 0)], ids=lambda v: "x".join(str(i) for i in v) if isinstance(v, tuple) else "l%d" % v)
+@pytest.mark.parametrize("segb", [64, 2], ids=["whole-blocks", "split-blocks"])
 @pytest.mark.parametrize("N,C,traj,weighted", [((16, 16, 16), 2, "koosh", False), ((16, 26, 16), 4, "random", True),
                                                ((26, 16, 16), 6, "koosh", True), ((16, 16, 26), 8, "koosh", False),
                                                ((16, 16, 16), 16, "koosh", True), ((16, 16, 16), 20, "koosh", False)])
-def test_fused_tile_blocks(B, N, C, traj, weighted, segb, lanes, monkeypatch):
-    """Adjoint gridding on tile-block entries (csrc/kbtiles.cu, the few-coil formulation of coil-sharded operators):
-    every lane geometry, whole tiles and tiles cut into work items with the ordered fold (segment length forced
-    low so that the dense k-space centre of a small kooshball splits), with and without support windows."""
+def test_fused_block_gather(B, N, C, traj, weighted, segb, shape, lanes, monkeypatch):
+    """Matrix-free adjoint gridding on block entries (csrc/kbblocks.cu): every block shape and lane geometry, whole
+    blocks and blocks cut into work items with the ordered fold (segment length forced low so that the dense k-space
+    centre of a small kooshball splits), coil counts that need one and two chunks of 16 columns."""
     from indigo_b200 import fused
-    monkeypatch.setattr(fused.SenseDevice, "tiles_max_coils", 32)
+    monkeypatch.setattr(fused.SenseDevice, "block_shape", shape)
     monkeypatch.setattr(fused.SenseDevice, "tiles_seg_batches", segb)
     monkeypatch.setattr(fused.SenseDevice, "tiles_lanes", lanes)
     monkeypatch.setattr(fused.SenseDevice, "window_min_saving", 0.0)
     rs, coord, maps, w = _setup(N, C, traj, weighted)
     A = sense_operator_fused(B, N, coord, maps, 2.0, weights=w)
     d = A._dev
-    assert d.tiles is not None and d.runs is None and d.kb is not None and d.ksp_sorted
+    assert d.tiles is not None and d.tiles['shape'] == shape and d.runs is None and d.kb is not None and d.ksp_sorted
     if segb == 2 and traj == "koosh":
         assert d.tiles['nsplit'] > 0
     ref = osense.SenseOperator(N, coord, maps, 2.0, weights=w)
