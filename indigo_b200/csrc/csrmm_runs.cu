@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(128) run_fill_kernel(int64_t nruns, const int3
 // while it is in flight, and by the time a batch is needed it is a shared-memory read instead of an
 // L2/DRAM round trip in front of the dependent gathers (ncu: 22 % of the stall samples sat on the first
 // use of a register-prefetched batch, profiles/r01_s7_*).
-static const int kRingDepth = 5;
+static const int kRingDepth = 4;
 static const int kBatchBytes = 16 + 16 * kRunPad;
 
 __device__ __forceinline__ void run_issue_batch(unsigned char *slot, const int32_t *__restrict__ ids,
@@ -107,50 +107,10 @@ __device__ __forceinline__ void run_issue_batch(unsigned char *slot, const int32
     }
 }
 
-template <int PPL>
-__device__ __forceinline__ void run_weights(const unsigned char *sl, int p0, float (&w)[kRunPad][PPL]) {
-#pragma unroll
-    for (int u = 0; u < kRunPad; ++u) {
-        const unsigned char *wp = sl + 16 + 16 * u + 4 * p0;
-        if (PPL == 4) { const float4 v = *reinterpret_cast<const float4 *>(wp); w[u][0] = v.x; w[u][1 % PPL] = v.y; w[u][2 % PPL] = v.z; w[u][3 % PPL] = v.w; }
-        else if (PPL == 2) { const float2 v = *reinterpret_cast<const float2 *>(wp); w[u][0] = v.x; w[u][1 % PPL] = v.y; }
-        else w[u][0] = *reinterpret_cast<const float *>(wp);
-    }
-}
-
-__device__ __forceinline__ void run_gather(const unsigned char *sl, const char *xb, uint32_t xpitch_bytes, float4 (&x)[kRunPad]) {
-    const int4 id = *reinterpret_cast<const int4 *>(sl);
-    const int idv[kRunPad] = {id.x, id.y, id.z, id.w};
-#pragma unroll
-    for (int u = 0; u < kRunPad; ++u)
-        x[u] = __ldg(reinterpret_cast<const float4 *>(xb + (uint64_t)(uint32_t)idv[u] * xpitch_bytes));
-}
-
-template <int PPL>
-__device__ __forceinline__ void run_fma(const float4 (&x)[kRunPad], const float (&w)[kRunPad][PPL], pk2 (&acc)[PPL][2]) {
-#pragma unroll
-    for (int u = 0; u < kRunPad; ++u) {
-        const pk2 x0 = p_make(x[u].x, x[u].y), x1 = p_make(x[u].z, x[u].w);
-#pragma unroll
-        for (int t = 0; t < PPL; ++t) {
-            acc[t][0] = p_fma(p_bc(w[u][t]), x0, acc[t][0]);
-            acc[t][1] = p_fma(p_bc(w[u][t]), x1, acc[t][1]);
-        }
-    }
-}
-
 // acc[t][0..1] += sum over the run entries [a, b) of w_(p0+t) * X[id]  (two coils per lane, PPL of the run's four
 // points per lane starting at p0, b - a a multiple of 4).  ring: kRingDepth * kBatchBytes bytes of shared memory
 // owned by this lane group of GS lanes (gl = lane within the group); gmask: its lanes.
-//
-// MODE selects how the k-space gathers (one 16-byte load per entry and lane, addresses known only once the
-// entry's id has arrived) are kept ahead of the arithmetic:
-//   0  gathers of a batch are issued when the batch is consumed (round 1);
-//   1  as 0, plus prefetch.global.L2 of the NEXT batch's gather targets (the ring is waited on one batch
-//      further ahead): a DRAM round trip becomes an L2 hit by the time the gather is issued;
-//   2  the next batch's gathers are issued into a second set of registers before the current batch's FMAs
-//      (software pipeline: 16 more registers).
-template <int PPL, int MODE>
+template <int PPL>
 __device__ __forceinline__ void run_walk(int a, int b, const int32_t *__restrict__ ids, const float4 *__restrict__ w4,
                                          const char *xb, uint32_t xpitch_bytes, pk2 (&acc)[PPL][2],
                                          unsigned char *ring, int gl, int GS, int p0, unsigned gmask) {
@@ -161,53 +121,37 @@ __device__ __forceinline__ void run_walk(int a, int b, const int32_t *__restrict
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     }
     int slot = 0;
-    if (MODE == 2) {
-        float4 xn[kRunPad];
+    for (int k = 0; k < nb; ++k) {
         asm volatile("cp.async.wait_group %0;\n" ::"n"(kRingDepth - 1) : "memory");
         __syncwarp(gmask);
-        run_gather(ring, xb, xpitch_bytes, xn);
-        for (int k = 0; k < nb; ++k) {
-            const unsigned char *sl = ring + slot * kBatchBytes;
-            float4 x[kRunPad];
-#pragma unroll
-            for (int u = 0; u < kRunPad; ++u) x[u] = xn[u];
-            float w[kRunPad][PPL];
-            run_weights<PPL>(sl, p0, w);
-            const int nslot = slot + 1 == kRingDepth ? 0 : slot + 1;
-            if (k + 1 < nb) {
-                asm volatile("cp.async.wait_group %0;\n" ::"n"(kRingDepth - 2) : "memory");
-                __syncwarp(gmask);
-                run_gather(ring + nslot * kBatchBytes, xb, xpitch_bytes, xn);
-            }
-            __syncwarp(gmask);                                       // every lane has read slot k
-            if (k + kRingDepth < nb) run_issue_batch(ring + slot * kBatchBytes, ids, w4, a + (k + kRingDepth) * kRunPad, gl, GS);
-            asm volatile("cp.async.commit_group;\n" ::: "memory");
-            run_fma<PPL>(x, w, acc);
-            slot = nslot;
-        }
-        return;
-    }
-    for (int k = 0; k < nb; ++k) {
-        if (MODE == 1) asm volatile("cp.async.wait_group %0;\n" ::"n"(kRingDepth - 2) : "memory");
-        else           asm volatile("cp.async.wait_group %0;\n" ::"n"(kRingDepth - 1) : "memory");
-        __syncwarp(gmask);
         const unsigned char *sl = ring + slot * kBatchBytes;
+        const int4 id = *reinterpret_cast<const int4 *>(sl);
         float w[kRunPad][PPL];
-        run_weights<PPL>(sl, p0, w);
-        float4 x[kRunPad];
-        run_gather(sl, xb, xpitch_bytes, x);
-        const int nslot = slot + 1 == kRingDepth ? 0 : slot + 1;
-        if (MODE == 1 && k + 1 < nb) {
-            // one line of the sample's coil vector per 128 bytes: lanes 0-3 (and 8-11 of a 32-coil group) each take an id
-            const int32_t *nid = reinterpret_cast<const int32_t *>(ring + nslot * kBatchBytes);
-            for (int u = gl & 7; u < kRunPad; u += (GS < 8 ? GS : 8))
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + (uint64_t)(uint32_t)nid[u] * xpitch_bytes));
+#pragma unroll
+        for (int u = 0; u < kRunPad; ++u) {
+            const unsigned char *wp = sl + 16 + 16 * u + 4 * p0;
+            if (PPL == 4) { const float4 v = *reinterpret_cast<const float4 *>(wp); w[u][0] = v.x; w[u][1 % PPL] = v.y; w[u][2 % PPL] = v.z; w[u][3 % PPL] = v.w; }
+            else if (PPL == 2) { const float2 v = *reinterpret_cast<const float2 *>(wp); w[u][0] = v.x; w[u][1 % PPL] = v.y; }
+            else w[u][0] = *reinterpret_cast<const float *>(wp);
         }
+        float4 x[kRunPad];
+        const int idv[kRunPad] = {id.x, id.y, id.z, id.w};
+#pragma unroll
+        for (int u = 0; u < kRunPad; ++u)
+            x[u] = __ldg(reinterpret_cast<const float4 *>(xb + (uint64_t)(uint32_t)idv[u] * xpitch_bytes));
         __syncwarp(gmask);                                           // every lane has read the slot
         if (k + kRingDepth < nb) run_issue_batch(ring + slot * kBatchBytes, ids, w4, a + (k + kRingDepth) * kRunPad, gl, GS);
         asm volatile("cp.async.commit_group;\n" ::: "memory");
-        run_fma<PPL>(x, w, acc);
-        slot = nslot;
+#pragma unroll
+        for (int u = 0; u < kRunPad; ++u) {
+            const pk2 x0 = p_make(x[u].x, x[u].y), x1 = p_make(x[u].z, x[u].w);
+#pragma unroll
+            for (int t = 0; t < PPL; ++t) {
+                acc[t][0] = p_fma(p_bc(w[u][t]), x0, acc[t][0]);
+                acc[t][1] = p_fma(p_bc(w[u][t]), x1, acc[t][1]);
+            }
+        }
+        if (++slot == kRingDepth) slot = 0;
     }
 }
 
@@ -254,7 +198,7 @@ struct RunLanes {
 
 // Yil[rowmap[4*run + i]][c] = alpha * sum_e w_i(e) * Xil[id(e)][c]        (rowmap < 0: nothing stored)
 // Runs longer than seg_len are left to the segment kernels below.
-template <int CL, int PL, int MODE>
+template <int CL, int PL>
 __global__ void __launch_bounds__(256) csrmm_runs_kernel(int64_t nruns, int C, c64 alpha,
                                                          const int32_t *__restrict__ run_ptr,
                                                          const int32_t *__restrict__ ids, const float4 *__restrict__ w4,
@@ -290,13 +234,13 @@ __global__ void __launch_bounds__(256) csrmm_runs_kernel(int64_t nruns, int C, c
         pk2 acc[L::PPL][2];
 #pragma unroll
         for (int t = 0; t < L::PPL; ++t) { acc[t][0] = p_make(0.f, 0.f); acc[t][1] = p_make(0.f, 0.f); }
-        if (a < b) run_walk<L::PPL, MODE>(a, b, ids, w4, xb, xpitch_bytes, acc, ln.ring, ln.gl, L::GS, ln.p0, ln.gmask);
+        if (a < b) run_walk<L::PPL>(a, b, ids, w4, xb, xpitch_bytes, acc, ln.ring, ln.gl, L::GS, ln.p0, ln.gmask);
         if (coil_ok) run_store<L::PPL>(acc, alpha, rv, Yil, ypitch, ln.coil);
     }
 }
 
 // one lane group per segment of a split run: partial sums into scratch[seg][t][coil]
-template <int CL, int PL, int MODE>
+template <int CL, int PL>
 __global__ void __launch_bounds__(256) csrmm_runs_seg_kernel(int nseg, int C, const int4 *__restrict__ seg_desc,
                                                              const int32_t *__restrict__ ids,
                                                              const float4 *__restrict__ w4, const c64 *__restrict__ Xil,
@@ -311,7 +255,7 @@ __global__ void __launch_bounds__(256) csrmm_runs_seg_kernel(int nseg, int C, co
     pk2 acc[L::PPL][2];
 #pragma unroll
     for (int t = 0; t < L::PPL; ++t) { acc[t][0] = p_make(0.f, 0.f); acc[t][1] = p_make(0.f, 0.f); }
-    run_walk<L::PPL, MODE>(d.y, d.z, ids, w4, xb, xpitch_bytes, acc, ln.ring, ln.gl, L::GS, ln.p0, ln.gmask);
+    run_walk<L::PPL>(d.y, d.z, ids, w4, xb, xpitch_bytes, acc, ln.ring, ln.gl, L::GS, ln.p0, ln.gmask);
     if (ln.coil < C) {
 #pragma unroll
         for (int t = 0; t < L::PPL; ++t)
@@ -447,30 +391,24 @@ int ib200_ccsrmm_runs(void *stream, int64_t kp, int64_t ncols, float ar, float a
     const int cpitch = 2 * CL;                                       // scratch row: 2*CL complex words per point
     const size_t ring_bytes = (size_t)GPB * kRingDepth * kBatchBytes;
     const uint32_t pb = (uint32_t)(xpitch * sizeof(c64));
-#define IB200_RUNS_MODE_CASE(cl, pl, md)                                                                               \
-    {                                                                                                                  \
+#define IB200_RUNS_CASE(cl, pl)                                                                                        \
+    case (cl) * 8 + (pl):                                                                                              \
         if (ring_bytes > 48 * 1024) {                                                                                  \
-            IB200_TRY(cudaFuncSetAttribute(csrmm_runs_kernel<cl, pl, md>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes)); \
-            IB200_TRY(cudaFuncSetAttribute(csrmm_runs_seg_kernel<cl, pl, md>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes)); \
+            IB200_TRY(cudaFuncSetAttribute(csrmm_runs_kernel<cl, pl>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes)); \
+            IB200_TRY(cudaFuncSetAttribute(csrmm_runs_seg_kernel<cl, pl>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes)); \
         }                                                                                                              \
         if (nseg > 0) {                                                                                                \
             /* few, long, latency-bound lane groups: on the side stream, sharing the SMs with the main kernel */      \
             rc = side_stream_begin(s, &side);                                                                          \
             if (rc) return rc;                                                                                         \
-            csrmm_runs_seg_kernel<cl, pl, md><<<(unsigned)ceil_div(nseg, GPB), 256, ring_bytes, side>>>(nseg, (int)ncols, (const int4 *)seg_desc, ids, \
+            csrmm_runs_seg_kernel<cl, pl><<<(unsigned)ceil_div(nseg, GPB), 256, ring_bytes, side>>>(nseg, (int)ncols, (const int4 *)seg_desc, ids, \
                                                                                    (const float4 *)w4, (const c64 *)Xil, pb,  \
                                                                                    (c64 *)scratch, cpitch);           \
             count_launch();                                                                                            \
         }                                                                                                              \
-        csrmm_runs_kernel<cl, pl, md><<<(unsigned)blocks, 256, ring_bytes, s>>>(nruns, (int)ncols, alpha, run_ptr, ids, (const float4 *)w4, \
+        csrmm_runs_kernel<cl, pl><<<(unsigned)blocks, 256, ring_bytes, s>>>(nruns, (int)ncols, alpha, run_ptr, ids, (const float4 *)w4, \
                                                                (const c64 *)Xil, pb, (c64 *)Yil, ypitch, rowmap, seg_len, rpg); \
         if (nseg > 0) { rc = side_stream_end(s); if (rc) return rc; }                                                  \
-    }
-#define IB200_RUNS_CASE(cl, pl)                                                                                        \
-    case (cl) * 8 + (pl):                                                                                              \
-        if (mode == 1) IB200_RUNS_MODE_CASE(cl, pl, 1)                                                                 \
-        else if (mode == 2) IB200_RUNS_MODE_CASE(cl, pl, 2)                                                            \
-        else IB200_RUNS_MODE_CASE(cl, pl, 0)                                                                           \
         if (nsplit > 0) {                                                                                              \
             count_launch();                                                                                            \
             csrmm_runs_fold_kernel<cl, pl><<<(unsigned)ceil_div(nsplit, GPB), 256, 0, s>>>(nsplit, (int)ncols, alpha,  \
@@ -480,15 +418,12 @@ int ib200_ccsrmm_runs(void *stream, int64_t kp, int64_t ncols, float ar, float a
         break
     int rc = 0;
     cudaStream_t side = nullptr;
-    int mode = 0;                                                    // gather scheduling of run_walk (tuning knob, tools/)
-    if (const char *e = getenv("IB200_RUNS_MODE")) { const int v = atoi(e); if (v >= 0 && v <= 2) mode = v; }
     switch (CL * 8 + PL) {
         IB200_RUNS_CASE(1, 4); IB200_RUNS_CASE(1, 2); IB200_RUNS_CASE(1, 1); IB200_RUNS_CASE(2, 2); IB200_RUNS_CASE(2, 1);
         IB200_RUNS_CASE(4, 1); IB200_RUNS_CASE(8, 1); IB200_RUNS_CASE(16, 1);
         IB200_RUNS_CASE(32, 1);
         default: set_error("internal: no run gather for CL=%d PL=%d", CL, PL); return IB200_E_UNSUPPORTED;
     }
-#undef IB200_RUNS_MODE_CASE
 #undef IB200_RUNS_CASE
     IB200_LAUNCH_CHECK();
     return 0;

@@ -370,7 +370,7 @@ int ib200_kb_blocks_apply(void *stream, int64_t ncols, int by, int bz, float ar,
     IB200_REQUIRE(nsplit == 0 || (split && scratch && ((uintptr_t)scratch & 15) == 0), "split arrays missing");
     const c64 alpha = mk(ar, ai);
     cudaStream_t s = as_stream(stream);
-    int want = lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 ? lanes : (by * bz >= 16 ? 8 : 1);
+    int want = lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 ? lanes : (by * bz >= 16 ? 8 : (by * bz >= 4 ? 2 : 1));
     if (const char *e = getenv("IB200_BLOCKS_LANES")) {              // tuning knob (tools/)
         const int v = atoi(e);
         if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) want = v;

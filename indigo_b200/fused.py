@@ -48,7 +48,9 @@ class SenseDevice(object):
     run_long_thresh = 1024     # runs with more entries than this are cut into segments of this length
     allow_tiles = True         # adjoint gridding on block entries built from the separable records (csrc/kbblocks.cu)
     tiles_max_coils = 4        # whole 4x4x4 tiles up to this many coils (coil-sharded operators) ...
-    blocks_max_coils = 0       # ... 4x2x1 blocks up to this many; the x-runs of the stored adjoint above
+    blocks_max_coils = 64      # ... 4x2x2 blocks up to this many; the x-runs of the stored adjoint above
+                               # (measured at cfg3, profiles/r02_blocks.md: 2 coils 1.15 / 2.77 ms, 4: 2.0 / 3.0,
+                               #  8: 2.95 / 3.6, 16: 4.9 / 5.4 for blocks / x-runs)
     block_shape = None         # (by, bz) forced for every coil count (tests, tools/)
     tiles_seg_batches = 64     # blocks with more batches (of 4 entries) than this are cut into work items of this length
     tiles_lanes = 0            # lanes sharing the rows of a block (0: kernel default)
@@ -253,7 +255,7 @@ class SenseDevice(object):
         if self.C <= self.tiles_max_coils:
             return (4, 4)
         if self.C <= self.blocks_max_coils:
-            return (2, 1)
+            return (2, 2)
         return None
 
     def __del__(self):

@@ -85,7 +85,7 @@ def test_cfg3_full_size(B, C):
     A = sense_operator_fused(B, N, coord, maps, 2.0)
     d = A._dev
     assert d.kb is not None and d.win is not None and d.ksp_sorted
-    assert (d.tiles is not None) if C <= d.tiles_max_coils else (d.runs is not None)
+    assert d.tiles is not None and d.tiles['shape'] == ((4, 4) if C <= d.tiles_max_coils else (2, 2))
     assert 0.4 < d.support_fraction < 0.7                       # the kooshball covers the inscribed sphere
     err_f, err_a, err_adj, x, Ax = _check_operator(B, A, N, C, coord, maps, rs)
     assert err_f < TOL and err_a < TOL and err_adj < TOL, (err_f, err_a, err_adj)

@@ -43,7 +43,8 @@ def _setup(N, C, traj, weighted, seed=0):
     return rs, coord, maps, w
 
 
-@pytest.mark.parametrize("mode", ["separable", "separable-nowindows", "separable-unsorted", "real-packed", "complex"])
+@pytest.mark.parametrize("mode", ["separable", "separable-runs", "separable-nowindows", "separable-unsorted", "real-packed",
+                                  "complex"])
 @pytest.mark.parametrize("N,C,traj,weighted", CASES)
 def test_fused_against_oracle(B, N, C, traj, weighted, mode, monkeypatch):
     from indigo_b200 import fused
@@ -52,13 +53,16 @@ def test_fused_against_oracle(B, N, C, traj, weighted, mode, monkeypatch):
     monkeypatch.setattr(fused.SenseDevice, "allow_separable", mode.startswith("separable"))
     monkeypatch.setattr(fused.SenseDevice, "allow_windows", mode != "separable-nowindows")
     monkeypatch.setattr(fused.SenseDevice, "allow_runs", mode.startswith("separable"))
+    monkeypatch.setattr(fused.SenseDevice, "allow_tiles", mode != "separable-runs")
     monkeypatch.setattr(fused.SenseDevice, "allow_sorted_ksp", mode != "separable-unsorted")
     monkeypatch.setattr(fused.SenseDevice, "window_min_saving", 0.0)
     rs, coord, maps, w = _setup(N, C, traj, weighted)
     A = sense_operator_fused(B, N, coord, maps, 2.0, weights=w)
     assert A._dev.real == real
     assert (A._dev.kb is not None) == mode.startswith("separable")
-    assert A._dev.ksp_sorted == (mode in ("separable", "separable-nowindows") and C % 2 == 0)
+    assert A._dev.ksp_sorted == (mode in ("separable", "separable-runs", "separable-nowindows") and C % 2 == 0)
+    if mode.startswith("separable") and C % 2 == 0:
+        assert (A._dev.runs is not None) == (mode == "separable-runs") and (A._dev.tiles is None) == (mode == "separable-runs")
     if mode == "separable-nowindows":
         assert A._dev.win is None
     elif C % 2 == 0 and (C % 16 == 0 or 16 % C == 0):
@@ -199,7 +203,7 @@ def test_reduced_cfg4_32_coils_cg(B):
     N, C = (26, 26, 26), 32
     rs, coord, maps, w = _setup(N, C, "koosh", True, seed=5)
     A = sense_operator_fused(B, N, coord, maps, 2.0, weights=w)
-    assert A._dev.runs is not None and A._dev.kb is not None
+    assert A._dev.tiles is not None and A._dev.kb is not None
     AHA = normal_operator(A)
     ref = osense.SenseOperator(N, coord, maps, 2.0, weights=w)
     x = synth.rand64c(rs, int(np.prod(N)), 1)
