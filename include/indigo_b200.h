@@ -219,17 +219,13 @@ int ib200_ccsrmm_runs(void *stream, int64_t kp, int64_t ncols, float alpha_re, f
  *   ib200_kb_blocks_apply: Yil[rowmap[point]][c] = alpha * sum_e wz_e wy_e wx_e * Xil[out(e)][c] for an even
  *     number of at most 64 interleaved columns (served in chunks of 16); scratch: (work items of split blocks) *
  *     4*by*bz * 2*pow2ceil(min(ncols,16)/2) complex words; lanes: 0 or the number of lanes (1, 2, 4, 8, 16) that
- *     share the rows of a block; 32 with 4x4x4 blocks: the tensor-core form (3xTF32 mma.sync, one warp per work
- *     item) for every chunk whose column count is a multiple of 4 -- the lists must then have been built with
- *     batch_multiple = 2.
- * batch_multiple (1 or 2): every block's batch count and every work item's length is a multiple of it; seg_batches
- * must be one too.  The first two synchronise. */
+ *     share the rows of a block.
+ * The first two synchronise. */
 int ib200_kb_blocks_batch_bytes(int by, int bz);
 int ib200_kb_blocks_count(void *stream, int64_t m, const void *records, const int64_t grid[3], int by, int bz,
-                          const int32_t *rowmap, int seg_batches, int batch_multiple, int32_t *bptr, int32_t *wptr,
-                          int64_t *host_totals);
+                          const int32_t *rowmap, int seg_batches, int32_t *bptr, int32_t *wptr, int64_t *host_totals);
 int ib200_kb_blocks_fill(void *stream, int64_t m, const void *records, const int64_t grid[3], int by, int bz, int seg_batches,
-                         int batch_multiple, const int32_t *bptr, const int32_t *wptr, void *entries, int32_t *work, int32_t *split);
+                         const int32_t *bptr, const int32_t *wptr, void *entries, int32_t *work, int32_t *split);
 int ib200_kb_blocks_apply(void *stream, int64_t ncols, int by, int bz, float alpha_re, float alpha_im, int nwork,
                           const int32_t *work, const void *entries, const void *Xil, int64_t xpitch, void *Yil,
                           int64_t ypitch, const int32_t *rowmap, int nsplit, const int32_t *split, void *scratch, int lanes);

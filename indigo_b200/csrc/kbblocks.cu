@@ -80,8 +80,8 @@ __device__ __forceinline__ int block_id(int bx, int cy, int cz, BlockShape sh, i
 // work items of a block with nb batches: segments of seg_batches batches, lengthened for the densest blocks so that
 // no block has more than kTMaxSeg of them
 static const int kTMaxSeg = 48;
-__host__ __device__ __forceinline__ int block_seg_len(int nb, int seg_batches, int bm) {
-    const int cap = ((nb + kTMaxSeg - 1) / kTMaxSeg + bm - 1) / bm * bm;
+__host__ __device__ __forceinline__ int block_seg_len(int nb, int seg_batches) {
+    const int cap = (nb + kTMaxSeg - 1) / kTMaxSeg;
     return cap > seg_batches ? cap : seg_batches;
 }
 
@@ -123,18 +123,18 @@ __global__ void __launch_bounds__(128) block_pairs_emit_kernel(int64_t m, const 
 // batches and work items of every block; totals[0] += split blocks, totals[1] += work items of split blocks
 __global__ void __launch_bounds__(256) block_sizes_kernel(int64_t nblocks, const int32_t *__restrict__ bcnt,
                                                           const int32_t *__restrict__ rowmap, BlockShape sh, int seg_batches,
-                                                          int bm, int32_t *__restrict__ nbatch, int32_t *__restrict__ nwork,
+                                                          int32_t *__restrict__ nbatch, int32_t *__restrict__ nwork,
                                                           int *totals) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblocks) return;
-    const int nb = ((bcnt[b] + kTB - 1) / kTB + bm - 1) / bm * bm;      // whole batches, a multiple of bm of them
+    const int nb = (bcnt[b] + kTB - 1) / kTB;
     bool rows = false;
     for (int rr = 0; rr < sh.by * sh.bz; ++rr) {
         const int4 v = __ldg(reinterpret_cast<const int4 *>(rowmap + block_row((int)b, rr, sh.by, sh.bz)));
         rows = rows || v.x >= 0 || v.y >= 0 || v.z >= 0 || v.w >= 0;
     }
     int nw = 0;
-    if (rows) { const int sl = block_seg_len(nb, seg_batches, bm); nw = (nb + sl - 1) / sl; if (nw < 1) nw = 1; }
+    if (rows) { const int sl = block_seg_len(nb, seg_batches); nw = (nb + sl - 1) / sl; if (nw < 1) nw = 1; }
     nbatch[b] = rows ? nb : 0;
     nwork[b] = nw;
     if (nw > 1) { atomicAdd(totals, 1); atomicAdd(totals + 1, nw); }
@@ -182,19 +182,11 @@ __global__ void __launch_bounds__(128) block_fill_kernel(int64_t npairs, const i
         if (sh.has_wy()) for (int p = 0; p < sh.by; ++p) reinterpret_cast<float *>(base + sh.wy_off())[v * sh.by + p] = s * wy[p];
         if (sh.has_wz()) for (int p = 0; p < sh.bz; ++p) reinterpret_cast<float *>(base + sh.wz_off())[v * sh.bz + p] = s * wz[p];
     }
-    if (last) {                                                      // batches added to reach a multiple: zero weights
-        const int nbt = bptr[b + 1] - bptr[b];
-        for (int eb = kk / kTB + 1; eb < nbt; ++eb) {
-            unsigned char *pb = ent + ((int64_t)bptr[b] + eb) * sh.batch_bytes();
-            for (int v = 0; v < kTB; ++v) reinterpret_cast<int32_t *>(pb)[v] = q.out;
-            for (int o = 16; o < sh.batch_bytes(); o += 4) *reinterpret_cast<float *>(pb + o) = 0.f;
-        }
-    }
 }
 
 // work items {block, first batch, end batch, scratch slot or -1} and split descriptors {block, first slot, items, 0}
 __global__ void __launch_bounds__(256) block_work_kernel(int64_t nblocks, const int32_t *__restrict__ bptr,
-                                                         const int32_t *__restrict__ wptr, int seg_batches, int bm,
+                                                         const int32_t *__restrict__ wptr, int seg_batches,
                                                          int4 *__restrict__ work, int4 *__restrict__ split, int *cursors) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblocks) return;
@@ -204,7 +196,7 @@ __global__ void __launch_bounds__(256) block_work_kernel(int64_t nblocks, const 
     if (nw == 1) { work[w0] = make_int4((int)b, b0, b1, -1); return; }
     const int s0 = atomicAdd(cursors, nw);
     const int at = atomicAdd(cursors + 1, 1);
-    const int sl = block_seg_len(b1 - b0, seg_batches, bm);
+    const int sl = block_seg_len(b1 - b0, seg_batches);
     for (int j = 0; j < nw; ++j) {
         const int a = b0 + j * sl;
         work[w0 + j] = make_int4((int)b, a, a + sl < b1 ? a + sl : b1, s0 + j);
@@ -232,9 +224,6 @@ static bool blocks_grid_ok(const int64_t grid[3], int by, int bz, int64_t *nbloc
 }
 
 
-int dispatch_tiles_mma(int cc, cudaStream_t s, int nwork, c64 alpha, const int32_t *work, const void *entries, const c64 *X,
-                       uint32_t pb, c64 *Y, int64_t ypitch, const int32_t *rowmap, int nsplit, const int32_t *split,
-                       void *scratch);                                                   // kbblocks_mma.cu
 extern template int dispatch_coils<4, 4>(int, int, cudaStream_t, int, int, c64, const int32_t *, const void *, const c64 *, uint32_t, c64 *, int64_t, const int32_t *, int, const int32_t *, void *);
 extern template int dispatch_coils<2, 2>(int, int, cudaStream_t, int, int, c64, const int32_t *, const void *, const c64 *, uint32_t, c64 *, int64_t, const int32_t *, int, const int32_t *, void *);
 extern template int dispatch_coils<2, 1>(int, int, cudaStream_t, int, int, c64, const int32_t *, const void *, const c64 *, uint32_t, c64 *, int64_t, const int32_t *, int, const int32_t *, void *);
@@ -253,15 +242,12 @@ int ib200_kb_blocks_batch_bytes(int by, int bz) {
 }
 
 int ib200_kb_blocks_count(void *stream, int64_t m, const void *records, const int64_t grid[3], int by, int bz,
-                          const int32_t *rowmap, int seg_batches, int batch_multiple, int32_t *bptr, int32_t *wptr,
-                          int64_t *host_totals) {
+                          const int32_t *rowmap, int seg_batches, int32_t *bptr, int32_t *wptr, int64_t *host_totals) {
     int64_t nblocks = 0;
     int nt[3];
     IB200_REQUIRE(blocks_grid_ok(grid, by, bz, &nblocks, nt), "bad grid or block shape");
     IB200_REQUIRE(nblocks < (1LL << 31), "too many blocks");
     IB200_REQUIRE(m >= 0 && m < (1LL << 31) && seg_batches >= 1 && host_totals, "bad arguments");
-    IB200_REQUIRE((batch_multiple == 1 || batch_multiple == 2) && seg_batches % batch_multiple == 0,
-                  "segment length must be a multiple of the batch multiple (1 or 2)");
     IB200_REQUIRE(rowmap && bptr && wptr && (records || m == 0), "null pointer");
     for (int i = 0; i < 5; ++i) host_totals[i] = 0;
     const BlockShape sh{by, bz};
@@ -276,8 +262,7 @@ int ib200_kb_blocks_count(void *stream, int64_t m, const void *records, const in
                                                                            (int)grid[2], sh, nt[0], nt[1], nullptr, bcnt);
         count_launch();
     }
-    block_sizes_kernel<<<(unsigned)ceil_div(nblocks, 256), 256, 0, s>>>(nblocks, bcnt, rowmap, sh, seg_batches, batch_multiple, nbatch, nwork,
-                                                                          totals);
+    block_sizes_kernel<<<(unsigned)ceil_div(nblocks, 256), 256, 0, s>>>(nblocks, bcnt, rowmap, sh, seg_batches, nbatch, nwork, totals);
     count_launch();
     int rc = exclusive_scan_public(s, nblocks, nbatch, bptr);
     if (!rc) rc = exclusive_scan_public(s, nblocks, nwork, wptr);
@@ -300,13 +285,11 @@ int ib200_kb_blocks_count(void *stream, int64_t m, const void *records, const in
 }
 
 int ib200_kb_blocks_fill(void *stream, int64_t m, const void *records, const int64_t grid[3], int by, int bz, int seg_batches,
-                         int batch_multiple, const int32_t *bptr, const int32_t *wptr, void *entries, int32_t *work, int32_t *split) {
+                         const int32_t *bptr, const int32_t *wptr, void *entries, int32_t *work, int32_t *split) {
     int64_t nblocks = 0;
     int nt[3];
     IB200_REQUIRE(blocks_grid_ok(grid, by, bz, &nblocks, nt), "bad grid or block shape");
     IB200_REQUIRE(m >= 0 && m < (1LL << 31) && seg_batches >= 1, "bad arguments");
-    IB200_REQUIRE((batch_multiple == 1 || batch_multiple == 2) && seg_batches % batch_multiple == 0,
-                  "segment length must be a multiple of the batch multiple (1 or 2)");
     IB200_REQUIRE(bptr && wptr && entries && work && split && (records || m == 0), "null pointer");
     IB200_REQUIRE(((uintptr_t)entries & 15) == 0 && ((uintptr_t)work & 15) == 0 && ((uintptr_t)split & 15) == 0,
                   "block arrays must be 16-byte aligned");
@@ -359,8 +342,8 @@ int ib200_kb_blocks_fill(void *stream, int64_t m, const void *records, const int
     if (!rc && e == cudaSuccess) e = cudaMalloc(&cursors, 2 * sizeof(int));
     if (!rc && e == cudaSuccess) {
         cudaMemsetAsync(cursors, 0, 2 * sizeof(int), s);
-        block_work_kernel<<<(unsigned)ceil_div(nblocks, 256), 256, 0, s>>>(nblocks, bptr, wptr, seg_batches, batch_multiple,
-                                                                         (int4 *)work, (int4 *)split, cursors);
+        block_work_kernel<<<(unsigned)ceil_div(nblocks, 256), 256, 0, s>>>(nblocks, bptr, wptr, seg_batches, (int4 *)work,
+                                                                         (int4 *)split, cursors);
         count_launch();
         e = cudaStreamSynchronize(s);
     }
@@ -388,10 +371,9 @@ int ib200_kb_blocks_apply(void *stream, int64_t ncols, int by, int bz, float ar,
     const c64 alpha = mk(ar, ai);
     cudaStream_t s = as_stream(stream);
     int want = lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 ? lanes : (by * bz >= 16 ? 8 : (by * bz >= 4 ? 2 : 1));
-    bool mma = lanes == 32;                                          // tensor-core form (whole tiles, even batch counts)
     if (const char *e = getenv("IB200_BLOCKS_LANES")) {              // tuning knob (tools/)
         const int v = atoi(e);
-        if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) { want = v; mma = false; }
+        if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) want = v;
     }
     const uint32_t pb = (uint32_t)(xpitch * sizeof(c64));
     // chunks of at most 16 columns (8 coil lanes)
@@ -401,9 +383,7 @@ int ib200_kb_blocks_apply(void *stream, int64_t ncols, int by, int bz, float ar,
         const c64 *X = (const c64 *)Xil + c0;
         c64 *Y = (c64 *)Yil + c0;
         int rc = IB200_E_UNSUPPORTED;
-        if (by == 4 && bz == 4 && mma && cc % 4 == 0)
-            rc = dispatch_tiles_mma(cc, s, nwork, alpha, work, entries, X, pb, Y, ypitch, rowmap, nsplit, split, scratch);
-        else if (by == 4 && bz == 4) rc = dispatch_coils<4, 4>(CL, want, s, nwork, cc, alpha, work, entries, X, pb, Y, ypitch, rowmap, nsplit, split, scratch);
+        if (by == 4 && bz == 4) rc = dispatch_coils<4, 4>(CL, want, s, nwork, cc, alpha, work, entries, X, pb, Y, ypitch, rowmap, nsplit, split, scratch);
         else if (by == 2 && bz == 2) rc = dispatch_coils<2, 2>(CL, want, s, nwork, cc, alpha, work, entries, X, pb, Y, ypitch, rowmap, nsplit, split, scratch);
         else if (by == 2 && bz == 1) rc = dispatch_coils<2, 1>(CL, want, s, nwork, cc, alpha, work, entries, X, pb, Y, ypitch, rowmap, nsplit, split, scratch);
         else if (by == 1 && bz == 1) rc = dispatch_coils<1, 1>(CL, want, s, nwork, cc, alpha, work, entries, X, pb, Y, ypitch, rowmap, nsplit, split, scratch);

@@ -53,8 +53,7 @@ class SenseDevice(object):
                                #  8: 2.95 / 3.6, 16: 4.9 / 5.4 for blocks / x-runs)
     block_shape = None         # (by, bz) forced for every coil count (tests, tools/)
     tiles_seg_batches = 64     # blocks with more batches (of 4 entries) than this are cut into work items of this length
-    tiles_lanes = 0            # lanes sharing the rows of a block (0: kernel default; 32: tensor-core form of whole tiles)
-    tiles_mma_min_coils = 0    # whole tiles on the tensor cores (3xTF32 mma.sync) from this many coils on (0: never)
+    tiles_lanes = 0            # lanes sharing the rows of a block (0: kernel default)
     allow_windows = True       # k-space support windows: skip the grid outside the trajectory's support
     window_min_saving = 0.05   # ... when at least this fraction of the grid lies outside
 
@@ -69,8 +68,6 @@ class SenseDevice(object):
             self.tiles_max_coils = int(os.environ["IB200_TILES_MAXC"])
         if os.environ.get("IB200_BLOCKS_MAXC"):
             self.blocks_max_coils = int(os.environ["IB200_BLOCKS_MAXC"])
-        if os.environ.get("IB200_TILES_MMA"):
-            self.tiles_mma_min_coils = int(os.environ["IB200_TILES_MMA"])
         if os.environ.get("IB200_BLOCKS_SHAPE"):
             self.block_shape = tuple(int(v) for v in os.environ["IB200_BLOCKS_SHAPE"].split(","))
         if os.environ.get("IB200_TILES_SEG"):
@@ -203,26 +200,24 @@ class SenseDevice(object):
         shape = self._want_tiles()
         if self.real and self.kb is not None and shape:
             by, bz = shape
-            mma = bool(shape == (4, 4) and (int(self.tiles_lanes) == 32 or 0 < self.tiles_mma_min_coils <= C))
-            bm = 2 if mma else 1
-            segb = max(bm, int(self.tiles_seg_batches) // bm * bm)
+            segb = max(1, int(self.tiles_seg_batches))
             nblk = kp // 64 * (4 // by) * (4 // bz)
             bptr = B.empty_array((nblk + 1,), i32, name='G.H.blocks.batchptr')
             wptr = B.empty_array((nblk + 1,), i32, name='G.H.blocks.workptr')
             tot = (ctypes.c_int64 * 5)()
-            lib.kb_blocks_count(s, self.M, self.kb.ptr, grid3, by, bz, self.rowmap.ptr, segb, bm, bptr.ptr, wptr.ptr, tot)
+            lib.kb_blocks_count(s, self.M, self.kb.ptr, grid3, by, bz, self.rowmap.ptr, segb, bptr.ptr, wptr.ptr, tot)
             nbat, nwork, nsplit, nslot = int(tot[1]), int(tot[2]), int(tot[3]), int(tot[4])
             bb = int(lib.kb_blocks_batch_bytes(by, bz))
             ent = B.empty_array((max(nbat, 1) * bb // 8,), np.dtype('int64'), name='G.H.blocks.entries')
             work = B.empty_array((4 * max(nwork, 1),), i32, name='G.H.blocks.work')
             split = B.empty_array((4 * max(nsplit, 1),), i32, name='G.H.blocks.split')
-            lib.kb_blocks_fill(s, self.M, self.kb.ptr, grid3, by, bz, segb, bm, bptr.ptr, wptr.ptr, ent.ptr, work.ptr, split.ptr)
+            lib.kb_blocks_fill(s, self.M, self.kb.ptr, grid3, by, bz, segb, bptr.ptr, wptr.ptr, ent.ptr, work.ptr, split.ptr)
             cl = 1
             while cl < min(C, 16) // 2:
                 cl *= 2
             scratch = B.empty_array((max(nslot, 1) * 4 * by * bz * 2 * cl,), _C64, name='G.H.blocks.partial')
             self.tiles = dict(ent=ent, work=work, nwork=nwork, split=split, nsplit=nsplit, scratch=scratch,
-                              batches=nbat, bytes=nbat * bb, shape=(by, bz), lanes=32 if mma else int(self.tiles_lanes))
+                              batches=nbat, bytes=nbat * bb, shape=(by, bz))
             del bptr, wptr
         # x-run lists of the stored adjoint: one gather of a sample serves the four grid points of a tile row;
         # runs longer than run_long_thresh entries are cut into segments with their own lane groups
@@ -257,7 +252,7 @@ class SenseDevice(object):
             return None
         if self.block_shape:
             return tuple(self.block_shape)
-        if self.C <= self.tiles_max_coils or 0 < self.tiles_mma_min_coils <= self.C:
+        if self.C <= self.tiles_max_coils:
             return (4, 4)
         if self.C <= self.blocks_max_coils:
             return (2, 2)
@@ -317,7 +312,7 @@ class SenseDevice(object):
             t = self.tiles
             lib.kb_blocks_apply(s, self.C, t['shape'][0], t['shape'][1], 1.0, 0.0, t['nwork'], t['work'].ptr, t['ent'].ptr,
                                 self.ksp.ptr, self.C, self.grid.ptr, self.C, self.rowmap.ptr, t['nsplit'], t['split'].ptr,
-                                t['scratch'].ptr, t['lanes'])
+                                t['scratch'].ptr, int(self.tiles_lanes))
         elif self.real and self.runs is not None:
             r = self.runs
             lib.ccsrmm_runs(s, self.kp, self.C, 1.0, 0.0, r['ptr'].ptr, r['ids'].ptr, r['w4'].ptr, self.ksp.ptr, self.C,
