@@ -43,6 +43,8 @@ def one(path):
             label = "kb_gather"
         elif "csrmm_runs" in name:
             label = "csrmm_runs"
+        elif "kb_blocks" in name:
+            label = "kb_blocks"
         elif "fft_pk" in name or "fft_il_pass" in name or "fft_spec" in name:
             label = order[min(npass, 3)]; npass += 1
         else:
