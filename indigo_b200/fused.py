@@ -52,7 +52,7 @@ class SenseDevice(object):
                                # (measured at cfg3, profiles/r02_blocks.md: 2 coils 1.15 / 2.77 ms, 4: 2.0 / 3.0,
                                #  8: 2.95 / 3.6, 16: 4.9 / 5.4 for blocks / x-runs)
     block_shape = None         # (by, bz) forced for every coil count (tests, tools/)
-    tiles_seg_batches = 64     # blocks with more batches (of 4 entries) than this are cut into work items of this length
+    tiles_seg_batches = 256    # blocks with more batches (of 4 entries) than this are cut into work items of this length
     tiles_lanes = 0            # lanes sharing the rows of a block (0: kernel default)
     allow_windows = True       # k-space support windows: skip the grid outside the trajectory's support
     window_min_saving = 0.05   # ... when at least this fraction of the grid lies outside

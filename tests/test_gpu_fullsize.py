@@ -97,7 +97,7 @@ def test_cfg3_full_size(B, C):
         # (c) six-call recipe on device-built CSR operands (generic ccsrmm / fftn kernels)
         del A, AHA, d
         Au = sense_operator_device(B, N, coord, maps, 2.0)
-        assert relerr(normal_operator(Au) * x, got) < 2e-6
+        assert relerr(normal_operator(Au) * x, got) < 5e-6      # stored float32(float64 product) weights vs three fp32 factors
 
 
 def test_cfg3_full_size_weighted_cg_step(B):
