@@ -54,6 +54,7 @@ class SenseDevice(object):
     block_shape = None         # (by, bz) forced for every coil count (tests, tools/)
     tiles_seg_batches = 256    # blocks with more batches (of 4 entries) than this are cut into work items of this length
     tiles_lanes = 0            # lanes sharing the rows of a block (0: kernel default)
+    keep_stored = False        # keep the CSR matrix and its stored adjoint after a matrix-free operator was built
     allow_windows = True       # k-space support windows: skip the grid outside the trajectory's support
     window_min_saving = 0.05   # ... when at least this fraction of the grid lies outside
 
@@ -243,6 +244,11 @@ class SenseDevice(object):
                              scratch=scratch, entries=int(nre.value))
         # zero-initialised: with windows, parts of the grid are never written, and the separable gather
         # multiplies its zero-weight taps (6th tap of on-grid samples) with whatever is there
+        if self.tiles is not None and self.kb is not None and not self.keep_stored:
+            # both gridding steps are matrix-free now: the CSR matrix, its stored adjoint and the long-row list were
+            # only the source of the support windows (17 GB at cfg3)
+            self.G = self.t_pk = self.t_ptr = self.t_val = self.t_ind = self.longrows = None
+            self.nlong = 0
         self.grid = B.zero_array((self.on * C,), _C64, name='grid[z][y][x][c]')
         self.ksp = B.empty_array((self.M * C,), _C64, name='ksp[m][c]')
 
