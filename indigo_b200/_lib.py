@@ -11,7 +11,7 @@ import os
 from ctypes import c_int, c_int64, c_float, c_double, c_void_p, c_char_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libindigo_b200.so")
+LIB_PATH = os.environ.get("IB200_LIB") or os.path.join(_HERE, "libindigo_b200.so")   # IB200_LIB: build variants (tools/)
 
 _vp, _i, _i64, _f = c_void_p, c_int, c_int64, c_float
 
