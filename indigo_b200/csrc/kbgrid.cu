@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(128) kb_records_kernel(int64_t m, const double
 }
 
 // (A packed-FFMA2 form of this row sum with incrementally stepped row pointers was measured in round 2,
-// profiles/r02_s2_cfg3.md: 14 % fewer warp instructions but IPC 2.0 -> 1.5 and 5.0 -> 5.9 ms at cfg3 -- the scalar
+// round 2, session 2: 14 % fewer warp instructions but IPC 2.0 -> 1.5 and 5.0 -> 5.9 ms at cfg3 -- the scalar
 // form below lets ptxas hoist the next row's loads over this row's FMAs within the 64-register budget.)
 // VC coils per lane: one 8-byte or one 16-byte load per tap
 template <int VC> struct KbVec;
