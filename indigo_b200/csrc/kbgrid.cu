@@ -16,7 +16,9 @@
 // of the three differs from the reference's float32 value by a few ulp (tests/test_gpu_fused.py
 // compares against the CSR product and the numpy oracle).  Only real-valued G' (grid extents that
 // make the centring phase +-1) and kernels of at most 6 taps per axis are served; anything else
-// stays on the stored-matrix path.
+// stays on the stored-matrix path.  On an axis shorter than the footprint (2-D problems are carried
+// with a two-point z axis) the taps alias; the record then holds the summed weight of every point
+// of the axis, where the reference's COO -> CSR conversion sums the duplicate entries.
 #include "common.cuh"
 #include "kb.cuh"
 #include "pk2.cuh"
@@ -46,17 +48,22 @@ __global__ void __launch_bounds__(128) kb_records_kernel(int64_t m, const double
         const int start = (int)ceil(__dsub_rn(pos, width));
         const int end = (int)floor(__dadd_rn(pos, width));
         int n = end - start;
-        if (n < 0 || n > kKbTaps || n > N) { atomicOr(flag, 1); n = n < 0 ? 0 : (N < kKbTaps ? N : kKbTaps); }
+        if (n < 0 || n > kKbTaps) { atomicOr(flag, 1); n = n < 0 ? 0 : kKbTaps; }
         int j = start % N; if (j < 0) j += N;
-        first[d] = j; cnt[d] = n;
+        first[d] = j;
+        // an axis shorter than the footprint (the two-point z axis of a 2-D problem): the taps alias onto its N points,
+        // tap t lands on point (first + t) mod N; the record holds the summed weights of the N points
+        const int np = n > N ? N : n;
+        cnt[d] = np;
+#pragma unroll
+        for (int t = 0; t < kKbTaps; ++t) w[t] = 0.f;
 #pragma unroll
         for (int t = 0; t < kKbTaps; ++t) {
-            float v = 0.f;
             if (t < n) {
                 const double wv = kb_lookup(table, ntab, fabs(__dsub_rn((double)(start + t), pos)) / width);
-                v = __fmul_rn((float)wv, f[j]);
+                const float v = __fmul_rn((float)wv, f[j]);
+                if (n > N) w[t % N] += v; else w[t] = v;
             }
-            w[t] = v;
             if (++j >= N) j = 0;
         }
     }
@@ -222,6 +229,7 @@ static int launch_kb_gather(cudaStream_t s, int64_t m, int C, c64 alpha, const K
     constexpr int SPW = 32 / CL;
     // ~32 samples per warp: long enough to amortise the launch of a CTA, short enough for >= 20 waves
     int iters = 32 / SPW; if (iters < 1) iters = 1;
+    if (m < (1 << 20)) iters = 1;                                    // small problems: more, shorter CTAs (latency-bound)
     const int64_t per_cta = (int64_t)8 * SPW * iters;
     const int64_t blocks = ceil_div(m, per_cta);
     IB200_REQUIRE(blocks < (1LL << 31), "too many samples for one launch");

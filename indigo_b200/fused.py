@@ -60,7 +60,7 @@ class SenseDevice(object):
 
     def __init__(self, B, N, coord, maps, oversamp=2.0, weights=None, width=3, n=128):
         import os
-        from .sense import gridding_matrix_device, _fftc_mod, kb_records_device
+        from .sense import gridding_matrix_device, _fftc_mod, kb_records_device, _fftc_unit_phase
         if os.environ.get("IB200_SAMPLE_SUPER"):                    # tuning knob: super-tile edge in tiles
             self.sample_super = (int(os.environ["IB200_SAMPLE_SUPER"]),) * 3
         if os.environ.get("IB200_SAMPLE_TILE"):                     # tuning knob: sample tile edge in grid points
@@ -79,6 +79,10 @@ class SenseDevice(object):
             # small problems (cfg1: 0.2 M samples) are bound by the longest serial walk of one lane group, not by
             # throughput: cut dense runs into shorter segments (r02 session 3: adjoint step 0.17 ms of a 0.37 ms apply)
             self.run_long_thresh = 256
+        if (int(np.prod(np.asarray(coord).shape[1:])) < (1 << 20) and type(self).tiles_seg_batches == 256
+                and not os.environ.get("IB200_TILES_SEG")):
+            self.tiles_seg_batches = 32                             # the same for the block gather (r02 session 18: cfg1
+                                                                    # 0.141 -> 0.049 ms; 16 and 64 batches are slower)
         from .kbmath import rolloff3
 
         self.B = B
@@ -88,7 +92,11 @@ class SenseDevice(object):
         if C > 32:
             raise RuntimeError("fused SENSE path serves at most 32 coils per operator; shard or split the coils")
         self._plan = None
-        self.G, oN, omin, beta = gridding_matrix_device(B, N, coord, oversamp, weights, width, n)
+        # centring phase of G' that is real only up to a unit constant (2-D problems: -i on the two-point z axis): the
+        # fused path holds conj(u) G', a real matrix, and applies u through alpha in the two gridding steps
+        os3 = oversamp if isinstance(oversamp, tuple) else (oversamp,) * 3
+        self.gphase = _fftc_unit_phase(tuple(int(a * o) for a, o in zip(N, os3))) or 1.0
+        self.G, oN, omin, beta = gridding_matrix_device(B, N, coord, oversamp, weights, width, n, unphase=self.gphase)
         self.N, self.oN, self.C = N, tuple(int(v) for v in oN), C
         self.M = int(self.G.shape[0])
         self.nvox, self.on = int(np.prod(N)), int(np.prod(oN))
@@ -299,7 +307,7 @@ class SenseDevice(object):
             self._samples_to_grid()
 
     def _grid_to_samples(self, alpha=1.0):
-        a = complex(alpha)
+        a = complex(alpha) * complex(self.gphase)
         G, lib, s = self.G, self.B._lib, self.B._stream
         if self.real and self.kb is not None:
             lib.kb_gather(s, self.M, self.C, a.real, a.imag, self.kb.ptr, self.grid.ptr, self.C,
@@ -314,22 +322,24 @@ class SenseDevice(object):
     def _samples_to_grid(self):
         lib, s = self.B._lib, self.B._stream
         lr = self.longrows.ptr if self.nlong else None
+        u = complex(self.gphase).conjugate()
+        ur, ui = float(u.real), float(u.imag)
         if self.real and self.tiles is not None:
             t = self.tiles
-            lib.kb_blocks_apply(s, self.C, t['shape'][0], t['shape'][1], 1.0, 0.0, t['nwork'], t['work'].ptr, t['ent'].ptr,
+            lib.kb_blocks_apply(s, self.C, t['shape'][0], t['shape'][1], ur, ui, t['nwork'], t['work'].ptr, t['ent'].ptr,
                                 self.ksp.ptr, self.C, self.grid.ptr, self.C, self.rowmap.ptr, t['nsplit'], t['split'].ptr,
                                 t['scratch'].ptr, int(self.tiles_lanes))
         elif self.real and self.runs is not None:
             r = self.runs
-            lib.ccsrmm_runs(s, self.kp, self.C, 1.0, 0.0, r['ptr'].ptr, r['ids'].ptr, r['w4'].ptr, self.ksp.ptr, self.C,
+            lib.ccsrmm_runs(s, self.kp, self.C, ur, ui, r['ptr'].ptr, r['ids'].ptr, r['w4'].ptr, self.ksp.ptr, self.C,
                             self.grid.ptr, self.C, self.rowmap.ptr, r['seg'], r['segd'].ptr, r['nseg'], r['spld'].ptr,
                             r['nsplit'], r['scratch'].ptr)
         elif self.real:
-            lib.ccsrmm_ilr(s, self.kp, self.M, self.C, self.nnz, 1.0, 0.0, self.t_pk.ptr, self.t_ptr.ptr,
+            lib.ccsrmm_ilr(s, self.kp, self.M, self.C, self.nnz, ur, ui, self.t_pk.ptr, self.t_ptr.ptr,
                            self.ksp.ptr, self.C, self.grid.ptr, self.C, self.rowmap.ptr, self.staged_adj, lr, self.nlong,
                            self.long_thresh)
         else:
-            lib.ccsrmm_il(s, self.kp, self.M, self.C, self.nnz, 1.0, 0.0, self.t_val.ptr, self.t_ind.ptr,
+            lib.ccsrmm_il(s, self.kp, self.M, self.C, self.nnz, ur, ui, self.t_val.ptr, self.t_ind.ptr,
                           self.t_ptr.ptr, self.ksp.ptr, self.C, self.grid.ptr, self.C, self.rowmap.ptr, 1,
                           lr, self.nlong, self.long_thresh)
 

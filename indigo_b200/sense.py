@@ -131,9 +131,11 @@ def _sample_weights(weights, m):
 
 
 
-def gridding_matrix_device(B, N, coord, oversamp=2.0, weights=None, width=3, n=128):
+def gridding_matrix_device(B, N, coord, oversamp=2.0, weights=None, width=3, n=128, unphase=None):
     """G' = interp * (mod * scale) built on the GPU straight into device CSR arrays
-    (ib200_kb_count -> exclusive scan -> ib200_kb_fill).  Returns (csr, oN, omin, beta)."""
+    (ib200_kb_count -> exclusive scan -> ib200_kb_fill).  Returns (csr, oN, omin, beta).
+    unphase (a unit constant u in {1, -1, i, -i}): build conj(u) * G' instead -- exact, and real when u is
+    _fftc_unit_phase(oN); the caller applies u through alpha."""
     import ctypes
     from scipy.signal.windows import kaiser
 
@@ -160,7 +162,10 @@ def gridding_matrix_device(B, N, coord, oversamp=2.0, weights=None, width=3, n=1
     nnz = int(g_ptr[m:m + 1].to_host()[0])
     g_ind = B.empty_array((max(nnz, 1),), np.dtype('int32'), name='interp*mod*scale.colInds')
     g_val = B.empty_array((max(nnz, 1),), _C64, name='interp*mod*scale.data')
-    colscale_d = B.copy_array(_fftc_mod_times_scale(oN))
+    colscale = _fftc_mod_times_scale(oN)
+    if unphase is not None and complex(unphase) != 1:
+        colscale = (colscale * np.complex64(np.conj(unphase))).astype(_C64)
+    colscale_d = B.copy_array(colscale)
     w_d = None
     if weights is not None:
         w_d = B.copy_array(_sample_weights(weights, m))
@@ -172,17 +177,40 @@ def gridding_matrix_device(B, N, coord, oversamp=2.0, weights=None, width=3, n=1
     return Gd, oN, omin, beta
 
 
-def _fftc_axis_factors(oN):
-    """Per-axis factors of mod*scale (backend.py:349-364): mod = prod_d exp(2 pi i (i_d - c_d/2) c_d/n_d).
-    Returns three float32 arrays (the scale folded into the last) when every factor is real to
-    rounding, else None."""
+def _fftc_unit_phases(oN):
+    """Per axis: (unit constant u_d in {1, -1, i, -i}, real factor array) with mod_d = u_d * factor_d, where
+    mod = prod_d exp(2 pi i (i_d - c_d/2) c_d/n_d) (backend.py:349-364); None when an axis is not real up to such a
+    constant.  Every even axis length gives u_d = 1 except n_d = 2 (mod 4 in general), whose factors are -i, +i:
+    the two-point z axis of a 2-D problem."""
     out = []
     for d in range(3):
         c = oN[d] // 2
         m = np.exp(1j * 2.0 * np.pi * ((np.arange(oN[d]) - c / 2.0) * (c / oN[d])))
-        if np.abs(m.imag).max() > 1e-6:
+        u = min((1, -1, 1j, -1j), key=lambda v: abs(m[0] - v))
+        r = m * np.conj(u)
+        if np.abs(r.imag).max() > 1e-6:
             return None
-        out.append(m.real.astype(np.float32))
+        out.append((complex(u), r.real.astype(np.float32)))
+    return out
+
+
+def _fftc_unit_phase(oN):
+    """Product of the per-axis unit constants (1 for every 3-D grid the fused path serves, -i for 2-D problems), or
+    None when the centring phase is not real up to a constant."""
+    ph = _fftc_unit_phases(oN)
+    if ph is None:
+        return None
+    u = complex(np.prod([p[0] for p in ph]))
+    return complex(round(u.real), round(u.imag))
+
+
+def _fftc_axis_factors(oN):
+    """Per-axis real factors of conj(u) * mod * scale (u = _fftc_unit_phase(oN)): three float32 arrays, the scale
+    folded into the last, or None when the centring phase is not real up to a constant."""
+    ph = _fftc_unit_phases(oN)
+    if ph is None:
+        return None
+    out = [p[1] for p in ph]
     scl = np.float32(np.complex64(np.complex128(1.0) / np.sqrt(int(np.prod(oN)))).real)
     out[2] = (out[2] * scl).astype(np.float32)
     return out

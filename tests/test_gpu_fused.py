@@ -272,13 +272,14 @@ def test_fused_matches_six_call_tree_at_size(B):
 def test_fused_two_dimensional_problem(B, C):
     """2-D problems are carried as N0 x N1 x 1 images (the reference's NUFFT is 3-D only, backend.py:404-405): the
     oversampled grid has a z axis of two points, served by the direct tiny-axis pass; the Kaiser-Bessel taps alias
-    onto the two planes, so the gridding steps run on stored entries (no separable records)."""
+    onto the two planes: the separable records hold the summed weights per plane (the reference's COO -> CSR conversion
+    sums the duplicates), so both gridding steps stay matrix-free."""
     N = (16, 16, 1)
     rs = np.random.RandomState(40 + C)
     coord = synth.radial_2d(nspokes=24, nread=32)
     maps = synth.unit_rss_maps(rs, N, C)
     A = sense_operator_fused(B, N, coord, maps, 2.0)
-    assert A._dev.oN == (32, 32, 2) and A._dev.kb is None
+    assert A._dev.oN == (32, 32, 2) and A._dev.kb is not None and A._dev.tiles is not None
     ref = osense.SenseOperator(N, coord, maps, 2.0)
     x = synth.rand64c(rs, int(np.prod(N)), 1)
     y = synth.rand64c(rs, ref.M * C, 1)
