@@ -469,6 +469,21 @@ def run_ours(args):
             "clocks": clk,
             "setup": {"seconds": round(setup_s, 1), "peak_bytes_per_gpu": setup_bytes, "resident_bytes_per_gpu": resident_bytes},
         }
+        try:
+            # the forward gather is bound by the L1 data path, not by HBM: one line request per tap,
+            # 128 bytes per clock and SM; reported next to the HBM figures when it is the dominant kernel
+            if dom["kernel"] == "kb_gather" and dev is not None and getattr(dev, "kb", None) is not None:
+                import torch as _t
+                prop = _t.cuda.get_device_properties(_t.cuda.current_device())
+                taps = 125.0 * dev.M * max(1, (8 * dev.C + 127) // 128)
+                l1_peak = 128.0 * prop.multi_processor_count * (clk["sm_mhz"] or 1965.0) * 1e6 / 1e9
+                l1_gbs = taps * 128.0 / (dom["ms"] * 1e-3) / 1e9
+                line["roofline"]["l1_path"] = {"line_requests": int(taps), "achieved": l1_gbs, "peak": l1_peak, "unit": "GB/s",
+                                               "frac": l1_gbs / l1_peak,
+                                               "note": "kb_gather: 125 taps per sample, one 128-byte line request each; "
+                                                       "128 B/clk/SM x SMs x measured SM clock"}
+        except Exception as exc:                        # never lose the line over an annotation
+            line["roofline"]["l1_path"] = {"error": str(exc)[:120]}
         if cg_info:
             line["cg"] = cg_info
         if check is not None:
