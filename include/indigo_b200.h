@@ -183,6 +183,18 @@ int ib200_kb_records(void *stream, int64_t m, const double *coord, const int64_t
                      const float *f2, const int32_t *perm, int out_is_record, void *records, int *host_flag);
 int ib200_kb_gather(void *stream, int64_t m, int64_t ncols, float alpha_re, float alpha_im, const void *records,
                     const void *grid_il, int64_t xpitch, const int64_t grid[3], void *Yil, int64_t ypitch);
+/* Matrix-free construction of the fused SENSE operator (no CSR matrix, no stored adjoint):
+ *   ib200_kb_sample_order: perm[r] = sample at position r when the samples are sorted (stably) by the two-level tile
+ *     rank (ib200_grid_tile_rank2 with the same tile / super extents) of their first tap -- the order
+ *     ib200_csr_permute_rows derives from the first column of every row of G'.
+ *   ib200_kb_support_windows: the windows of ib200_grid_support_windows from the separable records (the hull along z of
+ *     the taps of every record, zero-weight taps included, like the explicit zeros of the reference's matrix).
+ * Both synchronise. */
+int ib200_kb_sample_order(void *stream, int64_t m, const double *coord, const int64_t grid[3], double width,
+                          const int64_t tile[3], const int64_t super[3], int32_t *perm);
+int ib200_kb_support_windows(void *stream, int64_t m, const void *records, const int64_t grid[3], int64_t kp,
+                             const int32_t *rowmap, const int64_t block[3], int32_t *win, int32_t *rowmap_out,
+                             int64_t *host_inside);
 /* x-run form of a stored adjoint in tile-major row order (fused SENSE recipe, csrc/csrmm_runs.cu): the four
  * consecutive rows that form one x-row of a 4x4x4 tile are merged into one list of (sample, 4 weights)
  * entries, padded to a multiple of four entries.  ib200_csr_runs_count fills run_ptr[kp/4 + 1] and returns

@@ -50,6 +50,8 @@ SIGNATURES = {
     "ib200_kb_records": (_i, [_vp, _i64, _vp, POINTER(_i64), c_double, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp,
                               POINTER(_i)]),
     "ib200_kb_gather": (_i, [_vp, _i64, _i64, _f, _f, _vp, _vp, _i64, POINTER(_i64), _vp, _i64]),
+    "ib200_kb_sample_order": (_i, [_vp, _i64, _vp, POINTER(_i64), c_double, POINTER(_i64), POINTER(_i64), _vp]),
+    "ib200_kb_support_windows": (_i, [_vp, _i64, _vp, POINTER(_i64), _i64, _vp, POINTER(_i64), _vp, _vp, POINTER(_i64)]),
     "ib200_grid_support_windows": (_i, [_vp, POINTER(_i64), _i64, _vp, _vp, POINTER(_i64), _vp, _vp, POINTER(_i64)]),
     "ib200_sense_plan_set_support": (_i, [_vp, _vp, _i]),
     "ib200_csr_runs_count": (_i, [_vp, _i64, _vp, _vp, _i, _vp, POINTER(_i64), POINTER(_i), POINTER(_i)]),

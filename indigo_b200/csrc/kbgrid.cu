@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "kb.cuh"
 #include "pk2.cuh"
+#include <cub/device/device_radix_sort.cuh>
 
 namespace ib200 {
 
@@ -301,6 +302,61 @@ __global__ void __launch_bounds__(256) support_rowmap_kernel(int64_t kp, const i
     rowmap_out[r] = out;
 }
 
+// ---- matrix-free construction: sample order and support windows without the CSR matrix ---------------------
+// key of a sample = two-level tile rank (tile_rank2_kernel, csrmm_il.cu) of its first tap, computed from the
+// coordinates with the arithmetic of kb_records_kernel; rows[i] = i
+__global__ void __launch_bounds__(256) kb_base_key_kernel(int64_t m, const double *__restrict__ coord, int N0, int N1,
+                                                          int N2, double width, int t0, int t1, int t2, int s0, int s1,
+                                                          int s2, int32_t *__restrict__ keys, int32_t *__restrict__ rows) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    int c[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const int N = d == 0 ? N0 : d == 1 ? N1 : N2;
+        const double pos = __dadd_rn(__dmul_rn((double)N, coord[3 * i + d]), (double)(N / 2));
+        int j = (int)ceil(__dsub_rn(pos, width)) % N; if (j < 0) j += N;
+        c[d] = j;
+    }
+    const int nt0 = (N0 + t0 - 1) / t0, nt1 = (N1 + t1 - 1) / t1;
+    const int ns0 = (nt0 + s0 - 1) / s0, ns1 = (nt1 + s1 - 1) / s1;
+    const int tvol = t0 * t1 * t2, svol = s0 * s1 * s2;
+    const int tx = c[0] / t0, ty = c[1] / t1, tz = c[2] / t2;
+    const int64_t super = ((int64_t)(tz / s2) * ns1 + ty / s1) * ns0 + tx / s0;
+    const int intile = ((c[2] % t2) * t1 + (c[1] % t1)) * t0 + (c[0] % t0);
+    const int insuper = ((tz % s2) * s1 + (ty % s1)) * s0 + (tx % s0);
+    keys[i] = (int32_t)((super * svol + insuper) * tvol + intile);
+    rows[i] = (int32_t)i;
+}
+
+// hull along z of the grid points every record touches, per block of bx x by grid columns (what support_mark_kernel
+// derives from the rows of the stored adjoint)
+__global__ void __launch_bounds__(256) support_mark_records_kernel(int64_t m, const KbRecord *__restrict__ rec, int n0,
+                                                                   int n1, int n2, int bx, int by, int tz, int nbx,
+                                                                   int32_t *lo, int32_t *hi) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    const KbRecord *q = rec + r;
+    const int nt = q->ntaps, nx = nt & 255, ny = (nt >> 8) & 255, nz = (nt >> 16) & 255;
+    if (nx == 0 || ny == 0 || nz == 0) return;
+    int zl = 0x7fffffff, zh = 0, z = q->iz0;
+    for (int k = 0; k < nz; ++k) {
+        const int l = (z / tz) * tz; int h = l + tz; if (h > n2) h = n2;
+        zl = l < zl ? l : zl; zh = h > zh ? h : zh;
+        if (++z >= n2) z = 0;
+    }
+    int y = q->iy0;
+    for (int j = 0; j < ny; ++j) {
+        int x = q->ix0, last = -1;
+        for (int i = 0; i < nx; ++i) {
+            const int b = (y / by) * nbx + x / bx;
+            if (b != last) { atomicMin(lo + b, zl); atomicMax(hi + b, zh); last = b; }
+            if (++x >= n0) x = 0;
+        }
+        if (++y >= n1) y = 0;
+    }
+}
+
 static int kb_pow2_ceil(int64_t v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 }  // namespace ib200
@@ -361,6 +417,81 @@ int ib200_grid_support_windows(void *stream, const int64_t grid[3], int64_t kp, 
     support_init_kernel<<<(unsigned)ceil_div(nb, 256), 256, 0, s>>>(nb, lo, hi);
     if (kp > 0)
         support_mark_kernel<<<(unsigned)ceil_div(kp, 256), 256, 0, s>>>(kp, rowptr, rowmap, n0, n1, n2, bx, by, tz, nbx, lo, hi);
+    support_expand_kernel<<<(unsigned)ceil_div((int64_t)n0 * n1, 256), 256, 0, s>>>(n0, n1, bx, by, nbx, lo, hi, win, inside);
+    if (kp > 0)
+        support_rowmap_kernel<<<(unsigned)ceil_div(kp, 256), 256, 0, s>>>(kp, rowmap, n0, n1, win, rowmap_out);
+    count_launch(4);
+    unsigned long long h = 0;
+    cudaMemcpyAsync(&h, inside, sizeof(h), cudaMemcpyDeviceToHost, s);
+    e = cudaStreamSynchronize(s);
+    cudaFree(lo); cudaFree(inside);
+    IB200_TRY(e);
+    IB200_TRY(cudaGetLastError());
+    *host_inside = (int64_t)h;
+    return 0;
+}
+
+int ib200_kb_sample_order(void *stream, int64_t m, const double *coord, const int64_t grid[3], double width,
+                          const int64_t tile[3], const int64_t super[3], int32_t *perm) {
+    IB200_REQUIRE(m >= 0 && m < (1LL << 31) && grid && tile && super, "bad arguments");
+    if (m == 0) return 0;
+    IB200_REQUIRE(coord && perm && width > 0, "null pointer");
+    int64_t nranks = 1;
+    for (int d = 0; d < 3; ++d) {
+        IB200_REQUIRE(grid[d] > 0 && tile[d] > 0 && tile[d] <= 64 && super[d] > 0 && super[d] <= 64, "bad grid / tile extent");
+        nranks *= ceil_div(ceil_div(grid[d], tile[d]), super[d]) * super[d] * tile[d];
+    }
+    IB200_REQUIRE(nranks < (1LL << 31), "padded grid must hold fewer than 2^31 points");
+    cudaStream_t s = as_stream(stream);
+    int32_t *buf = nullptr;
+    IB200_TRY(cudaMalloc(&buf, (size_t)m * sizeof(int32_t) * 4));
+    int32_t *keys_a = buf, *keys_b = buf + m, *rows_a = buf + 2 * m, *rows_b = buf + 3 * m;
+    kb_base_key_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, s>>>(m, coord, (int)grid[0], (int)grid[1], (int)grid[2], width,
+                                                                 (int)tile[0], (int)tile[1], (int)tile[2], (int)super[0],
+                                                                 (int)super[1], (int)super[2], keys_a, rows_a);
+    count_launch();
+    int end_bit = 1; while ((1LL << end_bit) <= nranks) ++end_bit;
+    cub::DoubleBuffer<int32_t> dk(keys_a, keys_b), dv(rows_a, rows_b);
+    size_t tmp_bytes = 0;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int)m, 0, end_bit, s);
+    void *tmp = nullptr;
+    if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16);
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, (int)m, 0, end_bit, s);
+    if (e == cudaSuccess) {
+        count_launch(end_bit / 8 + 2);
+        e = cudaMemcpyAsync(perm, dv.Current(), (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToDevice, s);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(tmp); cudaFree(buf);
+    IB200_TRY(e);
+    IB200_TRY(cudaGetLastError());
+    return 0;
+}
+
+int ib200_kb_support_windows(void *stream, int64_t m, const void *records, const int64_t grid[3], int64_t kp,
+                             const int32_t *rowmap, const int64_t block[3], int32_t *win, int32_t *rowmap_out,
+                             int64_t *host_inside) {
+    IB200_REQUIRE(grid && block && host_inside, "null pointer");
+    *host_inside = 0;
+    IB200_REQUIRE(grid[0] > 0 && grid[1] > 0 && grid[2] > 0 && grid[0] * grid[1] < (1LL << 30), "bad grid");
+    IB200_REQUIRE(block[0] > 0 && block[1] > 0 && block[2] > 0, "bad block");
+    IB200_REQUIRE(kp >= 0 && kp < (1LL << 31) && m >= 0, "bad row count");
+    IB200_REQUIRE(rowmap && win && rowmap_out && (records || m == 0), "null pointer");
+    const int n0 = (int)grid[0], n1 = (int)grid[1], n2 = (int)grid[2];
+    const int bx = (int)block[0], by = (int)block[1], tz = (int)block[2];
+    const int nbx = (n0 + bx - 1) / bx, nby = (n1 + by - 1) / by, nb = nbx * nby;
+    cudaStream_t s = as_stream(stream);
+    int32_t *lo = nullptr;
+    unsigned long long *inside = nullptr;
+    IB200_TRY(cudaMalloc(&lo, (size_t)nb * 2 * sizeof(int32_t) + 16));
+    int32_t *hi = lo + nb;
+    cudaError_t e = cudaMalloc(&inside, sizeof(unsigned long long));
+    if (e != cudaSuccess) { cudaFree(lo); IB200_TRY(e); }
+    cudaMemsetAsync(inside, 0, sizeof(unsigned long long), s);
+    support_init_kernel<<<(unsigned)ceil_div(nb, 256), 256, 0, s>>>(nb, lo, hi);
+    if (m > 0)
+        support_mark_records_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, s>>>(m, (const KbRecord *)records, n0, n1, n2, bx, by,
+                                                                              tz, nbx, lo, hi);
     support_expand_kernel<<<(unsigned)ceil_div((int64_t)n0 * n1, 256), 256, 0, s>>>(n0, n1, bx, by, nbx, lo, hi, win, inside);
     if (kp > 0)
         support_rowmap_kernel<<<(unsigned)ceil_div(kp, 256), 256, 0, s>>>(kp, rowmap, n0, n1, win, rowmap_out);

@@ -54,6 +54,7 @@ class SenseDevice(object):
     block_shape = None         # (by, bz) forced for every coil count (tests, tools/)
     tiles_seg_batches = 256    # blocks with more batches (of 4 entries) than this are cut into work items of this length
     tiles_lanes = 0            # lanes sharing the rows of a block (0: kernel default)
+    matrix_free_setup = True   # build the matrix-free operator without ever forming the CSR matrix or its stored adjoint
     keep_stored = False        # keep the CSR matrix and its stored adjoint after a matrix-free operator was built
     allow_windows = True       # k-space support windows: skip the grid outside the trajectory's support
     window_min_saving = 0.05   # ... when at least this fraction of the grid lies outside
@@ -95,12 +96,24 @@ class SenseDevice(object):
         # centring phase of G' that is real only up to a unit constant (2-D problems: -i on the two-point z axis): the
         # fused path holds conj(u) G', a real matrix, and applies u through alpha in the two gridding steps
         os3 = oversamp if isinstance(oversamp, tuple) else (oversamp,) * 3
-        self.gphase = _fftc_unit_phase(tuple(int(a * o) for a, o in zip(N, os3))) or 1.0
-        self.G, oN, omin, beta = gridding_matrix_device(B, N, coord, oversamp, weights, width, n, unphase=self.gphase)
-        self.N, self.oN, self.C = N, tuple(int(v) for v in oN), C
-        self.M = int(self.G.shape[0])
+        oN = tuple(int(a * o) for a, o in zip(N, os3))
+        omin = min(os3)
+        beta = np.pi * np.sqrt(((width * 2. / omin) * (omin - 0.5)) ** 2 - 0.8)       # as gridding_matrix_device
+        self.gphase = _fftc_unit_phase(oN) or 1.0
+        self.N, self.oN, self.C = N, oN, C
+        self.M = int(np.prod(np.asarray(coord).shape[1:]))
         self.nvox, self.on = int(np.prod(N)), int(np.prod(oN))
-        self.nnz = int(self.G.values.size)
+        # matrix-free construction: sample order from the coordinates, windows and block entries from the separable
+        # records; the CSR matrix G' (10 GB at cfg3), its transposition and their sorts are never made.  Anything the
+        # matrix-free kernels do not serve (odd coil counts, complex centring phase, wide kernels, switches off) takes the
+        # construction on stored matrices below.
+        mf = bool(self.matrix_free_setup and self.allow_real and self.allow_separable and self.allow_sorted_ksp
+                  and self.allow_tiles and not self.keep_stored and self._want_tiles() is not None and self.M > 0)
+        self.G = None
+        if not mf:
+            self.G, oN_, omin_, beta_ = gridding_matrix_device(B, N, coord, oversamp, weights, width, n, unphase=self.gphase)
+            assert tuple(int(v) for v in oN_) == oN
+            self.nnz = int(self.G.values.size)
         # fused plan first: raises RuntimeError (unsupported) for grids without specialised passes
         n3, on3 = (ctypes.c_int64 * 3)(*N), (ctypes.c_int64 * 3)(*self.oN)
         self._plan = ctypes.c_void_p()
@@ -121,17 +134,29 @@ class SenseDevice(object):
         colrank = B.empty_array((self.on,), i32)
         self.rowmap = B.empty_array((kp,), i32, name='G.H.rowmap')
         lib.grid_tile_rank(s, grid3, tile3, colrank.ptr, self.rowmap.ptr, ctypes.byref(padded))
-        self.t_ptr = B.empty_array((kp + 1,), i32, name='G.H.rowPtrs')
-        self.t_ind = B.empty_array((max(self.nnz, 1),), i32, name='G.H.colInds')
-        self.t_val = B.empty_array((max(self.nnz, 1),), _C64, name='G.H.data')
-        work = B.empty_array((kp + 1,), i32)
-        lib.csr_transpose_conj(s, self.M, kp, self.nnz, self.G.values.ptr, self.G.colInds.ptr, self.G.rowPtrs.ptr,
-                               self.t_val.ptr, self.t_ind.ptr, self.t_ptr.ptr, work.ptr, colrank.ptr)
-        del colrank, work
+        self.t_ptr = self.t_ind = self.t_val = self.t_pk = None
+        if not mf:
+            self.t_ptr = B.empty_array((kp + 1,), i32, name='G.H.rowPtrs')
+            self.t_ind = B.empty_array((max(self.nnz, 1),), i32, name='G.H.colInds')
+            self.t_val = B.empty_array((max(self.nnz, 1),), _C64, name='G.H.data')
+            work = B.empty_array((kp + 1,), i32)
+            lib.csr_transpose_conj(s, self.M, kp, self.nnz, self.G.values.ptr, self.G.colInds.ptr, self.G.rowPtrs.ptr,
+                                   self.t_val.ptr, self.t_ind.ptr, self.t_ptr.ptr, work.ptr, colrank.ptr)
+            del work
+        del colrank
         # real-weight packed entries (8 B instead of 12 B per stored entry, half the multiplies) when
         # the centring phase folded into G' is real, i.e. on every grid the fused path serves
         self.real, self.kb, self.ksp_sorted, self.pos = False, None, False, None
-        if self.nnz and self.allow_real:
+        if mf:
+            from .sense import sample_order_device
+            self.g_map, self.nnz = sample_order_device(B, self.oN, coord, width, self.sample_tile, self.sample_super)
+            self.kb = kb_records_device(B, self.oN, coord, beta, weights, width, n, perm=self.g_map, out_sorted=True)
+            if self.kb is not None:
+                self.real = self.ksp_sorted = True
+                self.pos = B.empty_array((max(self.M, 1),), i32, name='G.sorted.position')
+                lib.invert_perm(s, self.M, self.g_map.ptr, self.pos.ptr)
+                self.g_pk = self.g_ptr = None
+        elif self.nnz and self.allow_real:
             pk = np.dtype('int64')                                     # 8-byte (int32 column, float32 weight) records
             g_pk = B.zero_array((self.nnz + 2,), pk, name='G.packed')  # +2: the staged kernel copies 16-byte granules
             hmax = (ctypes.c_float * 2)()
@@ -177,7 +202,8 @@ class SenseDevice(object):
             del g_pk
         # rows of G'^H that are long enough to deserve a whole CTA (k-space centre of radial trajectories)
         cnt = ctypes.c_int()
-        lib.csr_long_rows(s, kp, self.t_ptr.ptr, self.long_thresh, None, 0, ctypes.byref(cnt))
+        if not mf:
+            lib.csr_long_rows(s, kp, self.t_ptr.ptr, self.long_thresh, None, 0, ctypes.byref(cnt))
         self.nlong, self.longrows = int(cnt.value), None
         if self.nlong:
             self.longrows = B.empty_array((self.nlong,), i32, name='G.H.longrows')
@@ -194,8 +220,14 @@ class SenseDevice(object):
                 rowmap_w = B.empty_array((kp,), i32, name='G.H.rowmap.support')
                 inside = ctypes.c_int64()
                 blk = (ctypes.c_int64 * 3)(bx, self.tile[1], self.tile[2])
-                lib.grid_support_windows(s, grid3, kp, self.t_ptr.ptr, self.rowmap.ptr, blk, win.ptr, rowmap_w.ptr,
-                                         ctypes.byref(inside))
+                if mf and self.kb is not None:
+                    lib.kb_support_windows(s, self.M, self.kb.ptr, grid3, kp, self.rowmap.ptr, blk, win.ptr, rowmap_w.ptr,
+                                           ctypes.byref(inside))
+                elif not mf:
+                    lib.grid_support_windows(s, grid3, kp, self.t_ptr.ptr, self.rowmap.ptr, blk, win.ptr, rowmap_w.ptr,
+                                             ctypes.byref(inside))
+                else:
+                    inside.value = self.on
                 frac = inside.value / float(self.on)
                 if frac <= 1.0 - self.window_min_saving:
                     try:
@@ -231,7 +263,7 @@ class SenseDevice(object):
         # x-run lists of the stored adjoint: one gather of a sample serves the four grid points of a tile row;
         # runs longer than run_long_thresh entries are cut into segments with their own lane groups
         self.runs = None
-        if self.tiles is None and self.real and self.allow_runs and C % 2 == 0 and self.tile[0] == 4 and kp % 4 == 0:
+        if not mf and self.tiles is None and self.real and self.allow_runs and C % 2 == 0 and self.tile[0] == 4 and kp % 4 == 0:
             seg = max(4, int(self.run_long_thresh) // 4 * 4)
             run_ptr = B.empty_array((kp // 4 + 1,), i32, name='G.H.runs.ptr')
             nre, nsg, nsp = ctypes.c_int64(), ctypes.c_int(), ctypes.c_int()
@@ -252,6 +284,12 @@ class SenseDevice(object):
                              scratch=scratch, entries=int(nre.value))
         # zero-initialised: with windows, parts of the grid are never written, and the separable gather
         # multiplies its zero-weight taps (6th tap of on-grid samples) with whatever is there
+        if mf and (self.kb is None or self.tiles is None):
+            # the records or the block entries could not be built (kernel wider than 6 taps): construct on stored matrices
+            lib.sense_plan_destroy(self._plan)
+            self._plan = None
+            self.matrix_free_setup = False
+            return self.__init__(B, N, coord, maps, oversamp, weights, width, n)
         if self.tiles is not None and self.kb is not None and not self.keep_stored:
             # both gridding steps are matrix-free now: the CSR matrix, its stored adjoint and the long-row list were
             # only the source of the support windows (17 GB at cfg3)

@@ -177,6 +177,27 @@ def gridding_matrix_device(B, N, coord, oversamp=2.0, weights=None, width=3, n=1
     return Gd, oN, omin, beta
 
 
+def sample_order_device(B, oN, coord, width, tile, super_):
+    """Matrix-free part of the fused operator's construction: (perm, nnz) with perm[r] = the sample at position r of
+    the tile-sorted order (ib200_kb_sample_order) and nnz = entries the gridding matrix would have (ib200_kb_count)."""
+    import ctypes
+    lib, s = B._lib, B._stream
+    c3 = np.asfortranarray(np.asarray(coord).reshape((3, -1), order='F').astype(np.float64))
+    m = c3.shape[1]
+    coord_d = B.copy_array(c3)
+    grid = (ctypes.c_int64 * 3)(*oN)
+    i32 = np.dtype('int32')
+    counts = B.empty_array((max(m, 1),), i32)
+    lib.kb_count(s, m, coord_d.ptr, grid, float(width), counts.ptr)
+    ptr = B.empty_array((m + 1,), i32)
+    lib.exclusive_scan_i32(s, m, counts.ptr, ptr.ptr)
+    nnz = int(ptr[m:m + 1].to_host()[0])
+    perm = B.empty_array((max(m, 1),), i32, name='G.sorted.rowmap')
+    lib.kb_sample_order(s, m, coord_d.ptr, grid, float(width), (ctypes.c_int64 * 3)(*tile), (ctypes.c_int64 * 3)(*super_),
+                        perm.ptr)
+    return perm, nnz
+
+
 def _fftc_unit_phases(oN):
     """Per axis: (unit constant u_d in {1, -1, i, -i}, real factor array) with mod_d = u_d * factor_d, where
     mod = prod_d exp(2 pi i (i_d - c_d/2) c_d/n_d) (backend.py:349-364); None when an axis is not real up to such a

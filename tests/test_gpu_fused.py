@@ -152,6 +152,40 @@ def test_fused_block_gather(B, N, C, traj, weighted, segb, shape, lanes, monkeyp
     np.testing.assert_array_equal(A.H * y, A.H * y)
 
 
+@pytest.mark.parametrize("N,C,traj,weighted", [((16, 16, 16), 2, "koosh", False), ((26, 26, 26), 16, "koosh", True),
+                                               ((16, 26, 16), 4, "random", True), ((16, 16, 1), 8, "radial2d", False)])
+def test_matrix_free_setup_matches_stored(B, N, C, traj, weighted, monkeypatch):
+    """The matrix-free construction (sample order from the coordinates, support windows and block entries from the
+    separable records: no CSR matrix, no stored adjoint) gives the same windows, row map and operator as the
+    construction on stored matrices."""
+    from indigo_b200 import fused
+    monkeypatch.setattr(fused.SenseDevice, "window_min_saving", 0.0)
+    if traj == "radial2d":
+        rs = np.random.RandomState(7)
+        coord, w = synth.radial_2d(nspokes=24, nread=32), None
+        maps = synth.unit_rss_maps(rs, N, C)
+    else:
+        rs, coord, maps, w = _setup(N, C, traj, weighted)
+    A = sense_operator_fused(B, N, coord, maps, 2.0, weights=w)
+    d = A._dev
+    assert d.G is None and d.t_ptr is None and d.tiles is not None and d.kb is not None
+    monkeypatch.setattr(fused.SenseDevice, "matrix_free_setup", False)
+    A2 = sense_operator_fused(B, N, coord, maps, 2.0, weights=w)
+    d2 = A2._dev
+    assert d2.tiles is not None and d2.nnz == d.nnz and d2.M == d.M
+    assert (d.win is None) == (d2.win is None)
+    if d.win is not None:
+        np.testing.assert_array_equal(d.win.to_host(), d2.win.to_host())
+        assert d.support_fraction == d2.support_fraction
+    np.testing.assert_array_equal(d.rowmap.to_host(), d2.rowmap.to_host())
+    ref = osense.SenseOperator(N, coord, maps, 2.0, weights=w)
+    x = synth.rand64c(rs, int(np.prod(N)), 1)
+    y = synth.rand64c(rs, ref.M * C, 1)
+    assert relerr(A * x, ref.forward(x)) < TOL and relerr(A.H * y, ref.adjoint(y)) < TOL
+    assert relerr(A * x, A2 * x) < 2e-6 and relerr(A.H * y, A2.H * y) < 2e-6
+    assert relerr(normal_operator(A) * x, ref.normal(x)) < TOL
+
+
 def test_fused_cg_iterates(B):
     """50 CG iterates of the well-conditioned protocol (sqrt-DCF rows, lamda = 0.05 ||A^H A||) on the
     reduced cfg3 geometry, fused operator vs the numpy oracle."""
